@@ -1,0 +1,78 @@
+// gan_track_b200 -- shared helpers for the sm_100a kernels behind the C ABI (include/gantrack_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+// dtype codes used across the C ABI.
+enum { GT_F32 = 0, GT_F16 = 1, GT_F64 = 2 };
+
+// ---- error handling: return code + thread-local message (SURVEY.md section 8b "Errors") -------------------------
+#define GT_OK 0
+#define GT_ERR_ARG 1
+#define GT_ERR_CUDA 2
+#define GT_ERR_UNSUPPORTED 3
+
+void gt_set_error(const char* fmt, ...);
+
+#define GT_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            gt_set_error(__VA_ARGS__);        \
+            return GT_ERR_ARG;                \
+        }                                     \
+    } while (0)
+
+#define GT_CUDA_LAUNCH_CHECK(name)                                                        \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            gt_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));    \
+            return GT_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+// ---- device properties (cached per process; the library keeps no other global state) ---------------------------
+int gt_num_sms();
+
+// ---- scalar type traits: I/O type -> accumulation type (fp16 I/O computes in fp32, like OPS/bias_act.cu:15-18) --
+template <class T> struct Acc { typedef float type; };
+template <> struct Acc<double> { typedef double type; };
+
+template <class T> __device__ __forceinline__ typename Acc<T>::type to_acc(T v) { return (typename Acc<T>::type)v; }
+template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
+
+template <class T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v) { return (T)v; }
+template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half_rn(v); }
+
+// ---- 16-byte vector I/O ---------------------------------------------------------------------------------------
+template <class T> struct Vec16 { static constexpr int N = 16 / sizeof(T); T v[16 / sizeof(T)]; };
+
+template <class T> __device__ __forceinline__ Vec16<T> ld16(const T* p) {
+    Vec16<T> r;
+    *reinterpret_cast<uint4*>(r.v) = *reinterpret_cast<const uint4*>(p);
+    return r;
+}
+// streaming (read-once) load: bypass L1 allocation
+template <class T> __device__ __forceinline__ Vec16<T> ld16_stream(const T* p) {
+    Vec16<T> r;
+    uint4 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+    *reinterpret_cast<uint4*>(r.v) = u;
+    return r;
+}
+template <class T> __device__ __forceinline__ void st16(T* p, const Vec16<T>& r) {
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(r.v);
+}
+template <class T> __device__ __forceinline__ void st16_stream(T* p, const Vec16<T>& r) {
+    uint4 u = *reinterpret_cast<const uint4*>(r.v);
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,51 @@
+"""The three convolution primitives behind `conv2d_gradfix`: forward / data-gradient (same kernel family) and
+weight-gradient.
+
+Coverage (see DESIGN.md "conv" for the table that is kept current):
+  * fp16, channels-last, groups == 1, Cin and Cout multiples of 64: tcgen05 implicit GEMM (csrc/conv_igemm.cu)
+    - 3x3 stride 1 pad 1, 1x1 stride 1, 3x3 stride 2 pad 0 (D down path), 3x3 transposed stride 2 (G up path).
+  * everything else on the path (fp32 low-resolution layers, 1-channel ToRGB / FromRGB, grouped eval-mode convs,
+    weight gradients until the tcgen05 wgrad lands) is routed to the library convolution of the host framework
+    (`aten::convolution` -> cuDNN), exactly what the reference itself calls (OPS/conv2d_gradfix.py:40,45).  The
+    route taken is counted in `stats` so tests and bench.py can report how many launches were ours.
+"""
+import torch
+
+from ... import _lib
+
+stats = {'igemm': 0, 'library': 0, 'library_wgrad': 0, 'igemm_wgrad': 0}
+
+# Set by conv_igemm (if the kernels are available) -- callables returning None when a shape is not covered.
+_igemm_forward = None
+_igemm_wgrad = None
+
+allow_igemm = True
+
+
+def _aten_conv(x, w, stride, padding, transpose, output_padding, groups):
+    return torch.ops.aten.convolution(x, w, None, list(stride), list(padding), [1, 1], transpose, list(output_padding), groups)
+
+
+def conv_forward(x, w, *, transpose, output_padding, stride, padding, groups):
+    _lib.require_cuda(x, 'conv input')
+    if allow_igemm and _igemm_forward is not None:
+        y = _igemm_forward(x, w, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
+        if y is not None:
+            stats['igemm'] += 1
+            return y
+    stats['library'] += 1
+    return _aten_conv(x, w, stride, padding, transpose, output_padding, groups)
+
+
+def conv_wgrad(dy, x, weight_shape, *, transpose, output_padding, stride, padding, groups):
+    _lib.require_cuda(x, 'conv input')
+    if allow_igemm and _igemm_wgrad is not None:
+        dw = _igemm_wgrad(dy, x, weight_shape, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
+        if dw is not None:
+            stats['igemm_wgrad'] += 1
+            return dw
+    stats['library_wgrad'] += 1
+    w_dummy = torch.empty(weight_shape, dtype=x.dtype, device=x.device)
+    _, dw, _ = torch.ops.aten.convolution_backward(dy, x, w_dummy, None, list(stride), list(padding), [1, 1], transpose,
+                                                   list(output_padding), groups, [False, True, False])
+    return dw

@@ -1,0 +1,77 @@
+/* gantrack_b200.h -- C ABI of libgantrack_b200.so: the sm_100a kernels behind Gan-track's StyleGAN2-ADA op surface.
+ *
+ * This is the drop-in boundary.  In the reference the boundary is two pybind modules that are
+ * JIT-built and loaded by `custom_ops.get_plugin` (S3/torch_utils/custom_ops.py:59-155, S3 =
+ * /root/reference/src/models/stylegan3):
+ *     bias_act_plugin.bias_act(...)    OPS/bias_act.cpp:32, 94-97
+ *     upfirdn2d_plugin.upfirdn2d(...)  OPS/upfirdn2d.cpp:16, 102-105
+ * and, for everything GEMM-shaped, calls into cuDNN through torch (OPS/conv2d_gradfix.py:40,45).  Here every entry
+ * point is plain C: raw device pointers, sizes and strides in ELEMENTS, a CUDA stream handle, an int status.
+ *
+ * Conventions
+ *   - Every function returns 0 on success; on failure a non-zero code, and gt_last_error() (thread-local text)
+ *     says why.  The Python binding turns that into RuntimeError, as TORCH_CHECK does in the reference.
+ *   - The library owns no memory and keeps no mutable global state (only cached device attributes).  The caller
+ *     allocates every output and workspace (torch.empty in the binding, so memory stays in the caching allocator).
+ *   - All pointers are device pointers on the CURRENT device; `stream` is a cudaStream_t of that device.  Entry
+ *     points are re-entrant: the autograd engine calls them from its own thread.
+ *   - dtype codes: GT_F32 = 0, GT_F16 = 1, GT_F64 = 2.  fp16 I/O always computes in fp32.
+ *   - No entry point falls back to a CPU or library implementation; unsupported arguments are an error.
+ */
+#ifndef GANTRACK_B200_H_
+#define GANTRACK_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GT_DTYPE_F32 0
+#define GT_DTYPE_F16 1
+#define GT_DTYPE_F64 2
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* gt_last_error(void);
+/* ABI revision of this header. */
+int gt_abi_version(void);
+/* Number of SMs of the current device (148 on B200). */
+int gt_sm_count(void);
+
+/* ---- bias_act ---------------------------------------------------------------------------------------------------
+ * Replaces `bias_act_plugin.bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`
+ * (OPS/bias_act.cpp:32-90; kernel OPS/bias_act.cu:23-146).
+ *   grad = 0: y = clamp(act(x + b) * gain)
+ *   grad = 1: y = x * gain * act'(.) * [|yref| < clamp]          (x is dy; act' decided from yref / xref)
+ *   grad = 2: y = x * gain * act''(.) * dy * [|yref| < clamp]    (x is d_dx)
+ * x, xref, yref, dy, y: `size_x` dense elements in the same layout.  b: `size_b` elements or NULL; the bias of element
+ * i is b[(i / step_b) % size_b] (step_b = stride of the bias dim: H*W for NCHW, 1 for channels-last / matrices).
+ * act: 1 linear, 2 relu, 3 lrelu, 4 tanh, 5 sigmoid, 6 elu, 7 selu, 8 softplus, 9 swish (OPS/bias_act.py:21-31).
+ * clamp < 0 disables clamping.  NULL for unused xref / yref / dy. */
+int gt_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y, int dtype,
+                int grad, int act, float alpha, float gain, float clamp, long long size_x, int size_b, long long step_b,
+                void* stream);
+
+/* Fused first-order backward for act in {linear, lrelu}: dx = grad-1 pass of dy AND db[c] = sum of dx over every
+ * dim but the bias dim, in one pass over memory (the reference runs `dx.sum(...)` as a second pass,
+ * OPS/bias_act.py:169-170).  The tensor is viewed as [outer, C, inner]: NCHW -> (N, C, H*W); channels-last or [N, C]
+ * matrices -> (rows, C, 1).  db is fp32[C].  The reduction order is fixed (deterministic).  workspace: fp32 scratch
+ * of at least gt_bias_act_bwd_workspace(outer, C, inner) floats. */
+long long gt_bias_act_bwd_workspace(int outer, int C, long long inner);
+int gt_bias_act_bwd(const void* dy, const void* yref, void* dx, float* db, float* workspace, long long workspace_floats,
+                    int dtype, int act, float alpha, float gain, float clamp, int outer, int C, long long inner,
+                    void* stream);
+
+/* ---- upfirdn2d --------------------------------------------------------------------------------------------------
+ * Replaces `upfirdn2d_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)`
+ * (OPS/upfirdn2d.cpp:16-98; kernels OPS/upfirdn2d.cu:29-200).  The caller computes the output size
+ *   OW = (W*upx + padx0 + padx1 - fw + downx) / downx,  OH likewise        (OPS/upfirdn2d.cpp:35-36)
+ * and allocates y.  x: [N,C,H,W] with element strides xs_*; y: [N,C,OH,OW] with strides ys_*; f: fp32 [fh,fw] with
+ * strides fs_*.  flip != 0 means correlation (taps used as stored); flip == 0 is true convolution. */
+int gt_upfirdn2d(const void* x, const float* f, void* y, int dtype, int N, int C, int H, int W, long long xs_n,
+                 long long xs_c, long long xs_h, long long xs_w, int fh, int fw, long long fs_h, long long fs_w, int OH,
+                 int OW, long long ys_n, long long ys_c, long long ys_h, long long ys_w, int upx, int upy, int downx,
+                 int downy, int padx0, int pady0, int flip, float gain, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANTRACK_B200_H_ */
