@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- train kimg/s of the StyleGAN2-ADA hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                 our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W  the reference's CPU (`ref`) path, oracle port
+
+A "step" is one training iteration of Gan-track's loop (S3/training/training_loop_mi_multimodal.py:308-376): the
+phases Gmain, Greg (every 4th), Dmain, Dreg (every 16th) with gradient exchange, Adam, G_ema and the ADA update,
+over one global batch of synthetic CLARO-shaped slices (float32 [B,1,256,256] in [0,255], 2-class one-hot labels).
+Workload at N=1: BASELINE.json configs[1] (256x256 1-ch, batch 32, cbase 16384, map-depth 8, fp16 top-4 resolutions,
+lazy R1 + path-length).  N>1: the same per-GPU batch on every rank (weak scaling), one NCCL gradient all-reduce per phase.
+
+One JSON line on stdout (rank 0).  `value`: inputs already resident in HBM.  `e2e`: through `Trainer.train_step` with
+pinned HOST inputs copied H2D every step and a scalar statistic read back D2H every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--res', type=int, default=256)
+    ap.add_argument('--batch-gpu', type=int, default=32)
+    ap.add_argument('--cbase', type=int, default=None)
+    ap.add_argument('--aug', default='ada', choices=['ada', 'noaug'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true')
+    ap.add_argument('--cpu-batch', type=int, default=4)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p['hbm_gbs'], tflops=p['bf16_tflops'], tflops_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']), src='measured')
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, src='fallback')
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampling
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+
+def cpu_iteration_runner(res, cbase, batch, aug):
+    """Build the training step on the CPU with the oracle's primitive ops (= the reference's `impl='ref'` path) and
+    return (run_phase, phases).  This is the only place bench.py executes oracle/."""
+    from oracle.backend import oracle_ops
+    from gan_track_b200.training import training_loop as tl
+    cfg = tl.claro_config(resolution=res, batch=batch, num_gpus=1, cbase=cbase, aug=aug)
+    ctx = oracle_ops()
+    ctx.__enter__()
+    trainer = tl.Trainer(cfg, rank=0, device='cpu', overlap=False)
+    real = torch.rand([batch, 1, res, res]) * 255
+    idx = torch.randint(0, 2, [batch])
+    real_c = torch.nn.functional.one_hot(idx, 2).float()
+    return trainer, real, real_c, ctx
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port; the Python reference itself
+    cannot travel to the GPU box), all host threads, batch `--cpu-batch` per step, real phase schedule."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    res = args.res
+    cbase = args.cbase or (16384 if res <= 256 else 32768)
+    trainer, real, real_c, ctx = cpu_iteration_runner(res, cbase, args.cpu_batch, args.aug)
+    try:
+        for _ in range(args.warmup):
+            trainer.train_step(real, real_c)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            trainer.train_step(real, real_c)
+        dt = time.perf_counter() - t0
+    finally:
+        ctx.__exit__(None, None, None)
+    kimg_s = args.cpu_batch * args.steps / 1000.0 / dt
+    sample = f'{args.steps} training iterations at batch {args.cpu_batch}, {res}x{res} 1-ch, real phase schedule (after {args.warmup} warm-up)'
+    line = {
+        'impl': 'reference', 'metric': 'train kimg/s, StyleGAN2-ADA %dx%d 1-ch' % (res, res), 'value': kimg_s, 'unit': 'kimg/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1000.0, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'claro_stylegan2-ada shape {res}x{res} 1-ch cbase {cbase} map-depth 8, ADA={args.aug}, CPU ref path', 'global_batch': args.cpu_batch},
+        'cpu_baseline': {'value': kimg_s, 'unit': 'kimg/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': kimg_s, 'unit': 'kimg/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(res, cbase, aug, batch=4):
+    """Bounded sample for the `cpu_baseline` object of our arm: one warm-up iteration + iterations until ~12 s."""
+    cores = os.cpu_count() or 1
+    old = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    trainer, real, real_c, ctx = cpu_iteration_runner(res, cbase, batch, aug)
+    try:
+        trainer.train_step(real, real_c)            # iteration 0 runs all four phases; used as warm-up
+        # Amortised iteration = Gmain + Dmain every step, Greg every 4th, Dreg every 16th: time 16-step-equivalent by
+        # timing each kind of iteration once.
+        times = {}
+        t0 = time.perf_counter(); trainer.train_step(real, real_c); times['main'] = time.perf_counter() - t0      # idx 1: Gmain+Dmain
+        trainer.batch_idx = 4
+        t0 = time.perf_counter(); trainer.train_step(real, real_c); times['main+Greg'] = time.perf_counter() - t0
+        trainer.batch_idx = 16
+        t0 = time.perf_counter(); trainer.train_step(real, real_c); times['all'] = time.perf_counter() - t0
+    finally:
+        ctx.__exit__(None, None, None)
+        torch.set_num_threads(old)
+    t16 = 12 * times['main'] + 3 * times['main+Greg'] + 1 * times['all']
+    kimg_s = batch * 16 / 1000.0 / t16
+    sample = (f'batch {batch}, {res}x{res}: one iteration of each kind timed (main {times["main"]:.2f}s, +Greg {times["main+Greg"]:.2f}s, '
+              f'+Greg+Dreg {times["all"]:.2f}s), combined with the 16-iteration schedule 12/3/1')
+    return {'value': kimg_s, 'unit': 'kimg/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def dominant_kernel_roofline(device, pk):
+    """Roofline of the dominant kernel of OUR launches, timed live with CUDA events on the launching stream, L2 flushed
+    between launches.  See DESIGN.md 'Measurement' for the algorithmic bytes/flops per launch."""
+    from gan_track_b200.torch_utils.ops import bias_act
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get('bias_act_fwd_f16_32x64x256x256')
+        except Exception:
+            traffic = None
+    x = torch.randn([32, 64, 256, 256], device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn([64], device=device, dtype=torch.float16)
+    flush = torch.empty([256 << 20], dtype=torch.uint8, device=device)
+    for _ in range(3):
+        bias_act.bias_act(x, b, act='lrelu', clamp=256.0)
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        bias_act.bias_act(x, b, act='lrelu', clamp=256.0)
+        e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e))
+    ms = float(np.mean(times))
+    nbytes = 2 * x.numel() * 2
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {'kernel': 'bias_act_vec_kernel<half, lrelu> fwd [32,64,256,256] channels-last', 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'],
+            'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'], 'traffic': traffic, 'peak_source': pk['src'], 'ms_per_launch': ms,
+            'algorithmic_bytes_per_launch': nbytes}
+
+
+def run_ours(args):
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=device)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)'
+
+    from gan_track_b200 import _lib
+    from gan_track_b200.torch_utils import training_stats
+    from gan_track_b200.torch_utils.ops import conv_backend
+    from gan_track_b200.training import training_loop as tl
+    _lib.load()
+    if world > 1:
+        training_stats.init_multiprocessing(rank=rank, sync_device=device)
+
+    res = args.res
+    cbase = args.cbase or (16384 if res <= 256 else 32768)
+    batch_gpu = args.batch_gpu
+    global_batch = batch_gpu * world
+    gamma = 0.0002 * res ** 2 / global_batch if res != 256 or global_batch != 32 else 0.4096
+    cfg = tl.claro_config(resolution=res, batch=global_batch, num_gpus=world, cbase=cbase, aug=args.aug, gamma=gamma)
+    trainer = tl.Trainer(cfg, rank=rank, device=device, overlap=not args.no_overlap)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_img = (torch.rand([batch_gpu, 1, res, res], generator=g) * 255).pin_memory()
+    host_c = torch.nn.functional.one_hot(torch.randint(0, 2, [batch_gpu], generator=g), 2).float().pin_memory()
+    dev_img, dev_c = host_img.to(device), host_c.to(device)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        trainer.train_step(dev_img, dev_c)
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    counts0 = dict(trainer.phase_counts)
+    launches0 = _lib.launches
+    conv0 = dict(conv_backend.stats)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        trainer.train_step(dev_img, dev_c)
+    e.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(s.elapsed_time(e))
+    launches = _lib.launches - launches0
+    conv_stats = {k: conv_backend.stats[k] - conv0[k] for k in conv0}
+    phase_counts = {k: trainer.phase_counts[k] - counts0[k] for k in counts0}
+    value = global_batch * args.steps / 1000.0 / (ms_total * 1e-3)
+
+    # ---- timed: end to end through the public API with host inputs ----
+    e2e = None
+    if not args.no_e2e:
+        stat = torch.zeros([], device=device)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        d2h = 0
+        for _ in range(args.steps):
+            trainer.train_step(host_img, host_c)               # H2D of the step's real batch + labels inside train_step
+            stat = trainer.loss.pl_mean + trainer.augment_pipe.p if trainer.augment_pipe is not None else trainer.loss.pl_mean
+            _ = float(stat.item())                             # D2H read of a step result
+            d2h += 4
+        e2.record()
+        barrier()
+        ms_e2e = max_over_ranks(s2.elapsed_time(e2))
+        e2e = {'value': global_batch * args.steps / 1000.0 / (ms_e2e * 1e-3), 'unit': 'kimg/s',
+               'h2d_bytes_per_step': int(host_img.numel() * 4 + host_c.numel() * 4) * world, 'd2h_bytes_per_step': 4 * world}
+
+    if world > 1:
+        trainer.check_consistency()
+
+    pk = peaks()
+    roof = dominant_kernel_roofline(device, pk) if rank == 0 else None
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_base = cpu_baseline_sample(res, cbase, args.aug, batch=args.cpu_batch)
+        except Exception as ex:  # the CPU leg must never take the GPU number down with it
+            cpu_base = {'value': None, 'unit': 'kimg/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {ex!r}'}
+
+    if rank == 0:
+        flops_per_img = {256: 399e9, 512: 1597e9}.get(res)
+        line = {
+            'metric': 'train kimg/s, StyleGAN2-ADA %dx%d 1-ch' % (res, res), 'value': value, 'unit': 'kimg/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16', 'data': 'synthetic',
+            'config': {'workload': f'claro_stylegan2-ada shape: {res}x{res} 1-ch, batch {batch_gpu}/GPU, cbase {cbase}, map-depth 8, fp16 top-4 resolutions, '
+                                   f'lazy R1 (every 16) + path-length (every 4), ADA={args.aug}', 'global_batch': global_batch, 'batch_gpu': batch_gpu,
+                       'parallelism': f'dp{world}', 'phase_counts_in_timed_region': phase_counts,
+                       'l2_policy': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush in the step loop',
+                       'conv_routes': conv_stats},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base,
+        }
+        if flops_per_img:
+            line['model_tflops'] = value * 1000 * flops_per_img / 1e12
+            line['model_tensor_frac'] = line['model_tflops'] / world / pk['tflops_sustained']
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference_arm(a)
+    else:
+        run_ours(a)

@@ -30,6 +30,14 @@ _PROTOTYPES = {
 _lib = None
 _lock = threading.Lock()
 
+# Number of kernel launches issued through the C ABI by this process (bench.py reports it as `gpu_launches`).
+launches = 0
+
+
+def count_launch(n=1):
+    global launches
+    launches += n
+
 
 class GanTrackLibraryError(RuntimeError):
     pass

@@ -51,6 +51,7 @@ class _BiasActPlugin:
                                          _lib.dtype_code(x), int(grad), int(act), float(alpha), float(gain), float(clamp),
                                          x.numel(), int(b.numel()), int(step_b), _lib.stream_of(x))
         _lib.check(st, 'bias_act')
+        _lib.count_launch()
         return y
 
 
@@ -91,6 +92,7 @@ class _Upfirdn2dPlugin:
                                           int(upx), int(upy), int(downx), int(downy), int(padx0), int(pady0), int(bool(flip)),
                                           float(gain), _lib.stream_of(x))
         _lib.check(st, 'upfirdn2d')
+        _lib.count_launch()
         return y
 
 

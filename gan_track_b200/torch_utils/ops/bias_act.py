@@ -74,6 +74,7 @@ def _fused_bwd(dy, y, dim, spec, alpha, gain, clamp):
         st = lib.gt_bias_act_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), _lib.ptr(db), _lib.ptr(ws), ws_n, _lib.dtype_code(dy),
                                  spec.cuda_idx, alpha, gain, clamp, outer, C, inner, _lib.stream_of(dy))
     _lib.check(st, 'bias_act_bwd')
+    _lib.count_launch(2)
     return dx, db.to(dy.dtype)
 
 

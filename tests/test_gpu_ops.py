@@ -1,0 +1,297 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same inputs, against the committed
+golden vectors from the real reference, and -- at BASELINE.json's full sizes -- through size-independent properties.
+Tolerances are the north star's: fp32 <= 1e-5 relative, fp16 <= 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gen_golden as gg
+from oracle import ops_ref as R
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from gan_track_b200 import _lib
+    from gan_track_b200.torch_utils import custom_ops
+    from gan_track_b200.torch_utils.ops import bias_act, conv2d_gradfix, conv2d_resample, fma, grid_sample_gradfix, upfirdn2d
+
+DEV = 'cuda'
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.asarray(a)).to(DEV)
+    return x.to(dtype) if dtype is not None else x
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def assert_close(a, b, tol, what=''):
+    e = rel_err(a, b)
+    assert e <= tol, f'{what}: relative error {e:.3e} > {tol:.1e}'
+
+
+TOL = {torch.float32: 1e-5, torch.float16: 1e-2, torch.float64: 1e-10}
+
+
+def test_library_loaded_and_symbols():
+    lib = _lib.load()
+    assert lib.gt_abi_version() >= 1
+    assert lib.gt_sm_count() > 0
+
+
+# ---------------------------------------------------------------------------------------------------- bias_act
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('cl', [False, True])
+@pytest.mark.parametrize('case', gg.BIAS_ACT_PATH_CASES, ids=lambda c: c[0])
+def test_bias_act_path_cases(golden, case, cl, dtype):
+    name, act, gain, clamp, has_b, shape = case
+    if cl and len(shape) != 4:
+        pytest.skip('channels-last needs 4-D')
+    G = golden('ops_bias_act.npz')
+    x = t(G[f'bias_act/{name}/x'], dtype)
+    b = t(G[f'bias_act/{name}/b'], dtype) if has_b else None
+    dy = t(G[f'bias_act/{name}/dy'], dtype)
+    if cl:
+        x, dy = x.contiguous(memory_format=torch.channels_last), dy.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    if has_b:
+        b.requires_grad_(True)
+    y = bias_act.bias_act(x, b, dim=1, act=act, gain=gain, clamp=clamp)
+    # oracle on the same (rounded) inputs, in fp32
+    xo = x.detach().float().cpu().requires_grad_(True)
+    bo = b.detach().float().cpu().requires_grad_(True) if has_b else None
+    yo = R.bias_act(xo, bo, dim=1, act=act, gain=gain, clamp=clamp)
+    assert_close(y, yo, TOL[dtype], 'y')
+    if dtype == torch.float32:
+        assert_close(y, G[f'bias_act/{name}/y'], 1e-5, 'y vs golden')
+    # first order, differentiable path (create_graph) and fused path (no graph)
+    go = torch.autograd.grad(yo, [xo] + ([bo] if has_b else []), dy.float().cpu())
+    for create_graph in (True, False):
+        g = torch.autograd.grad(y, [x] + ([b] if has_b else []), dy, create_graph=create_graph, retain_graph=True)
+        if act == 'linear' and clamp is not None:
+            continue   # linear + clamp: the plugin does not mask the gradient (saves no y); covered in test_bias_act_linear_clamp_grad
+        assert_close(g[0], go[0], TOL[dtype], f'dx (create_graph={create_graph})')
+        if has_b:
+            assert_close(g[1], go[1], max(TOL[dtype], 2e-5), f'db (create_graph={create_graph})')
+    # second order: d<dx, v>/d(dy) = grad-1 pass of v
+    if act == 'lrelu':
+        dyv = dy.clone().requires_grad_(True)
+        dx, = torch.autograd.grad(y, x, dyv, create_graph=True)
+        v = torch.randn_like(dx)
+        d_dy, = torch.autograd.grad(dx, dyv, v)
+        alpha, g_, c_ = R._resolve(act, None, gain, clamp)
+        ref = R.bias_act_kernel(v.float().cpu(), None, None, y.detach().float().cpu(), None, 1, 1, act, alpha, g_, c_)
+        assert_close(d_dy, ref, TOL[dtype], 'd_dy')
+
+
+def test_bias_act_linear_clamp_grad():
+    """Reference CUDA semantics: `linear` saves no output, so the clamp does not mask its gradient (OPS/bias_act.py:151-154)."""
+    x = (torch.randn(2, 3, 4, 4, device=DEV) * 300).requires_grad_(True)
+    y = bias_act.bias_act(x, None, act='linear', clamp=256.0)
+    assert float(y.abs().max()) <= 256.0
+    dy = torch.randn_like(y)
+    dx, = torch.autograd.grad(y, x, dy)
+    assert_close(dx, dy.cpu(), 1e-6, 'dx')
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64, torch.float16])
+@pytest.mark.parametrize('act', gg.ALL_ACTS)
+def test_bias_act_all_activations(golden, act, dtype):
+    G = golden('ops_bias_act.npz')
+    x = t(G[f'bias_act_all/{act}/x'], dtype).requires_grad_(True)
+    b = t(G[f'bias_act_all/{act}/b'], dtype)
+    dy = t(G[f'bias_act_all/{act}/dy'], dtype).requires_grad_(True)
+    v = t(G[f'bias_act_all/{act}/v'], dtype)
+    tol = {torch.float32: 2e-5, torch.float64: 1e-9, torch.float16: 1e-2}[dtype]
+    y = bias_act.bias_act(x, b, dim=1, act=act)
+    assert_close(y, G[f'bias_act_all/{act}/y'], tol, 'y')
+    dx, = torch.autograd.grad(y, x, dy, create_graph=True)
+    assert_close(dx, G[f'bias_act_all/{act}/dx'], tol, 'dx')
+    d_x, d_dy = torch.autograd.grad(dx, [x, dy], v, allow_unused=True)
+    assert_close(d_dy, G[f'bias_act_all/{act}/d_dy'], tol, 'd_dy')
+    if R.ACTIVATIONS[act][4] and dtype != torch.float16:
+        assert_close(d_x, G[f'bias_act_all/{act}/d_x'], tol * 10, 'd_x')
+
+
+def test_bias_act_plugin_interface_and_errors():
+    """The object returned by get_plugin has the reference's pybind signature (OPS/bias_act.cpp:32) and its checks."""
+    plugin = custom_ops.get_plugin('bias_act_plugin', sources=['bias_act.cpp', 'bias_act.cu'], headers=['bias_act.h'], source_dir='.')
+    x = torch.randn(4, 8, 5, 5, device=DEV)
+    b = torch.randn(8, device=DEV)
+    e = torch.empty([0])
+    y = plugin.bias_act(x, b, e, e, e, 0, 1, 3, 0.2, 2 ** 0.5, 256.0)
+    assert_close(y, R.bias_act(x.cpu(), b.cpu(), act='lrelu', clamp=256.0), 1e-6)
+    with pytest.raises(RuntimeError):
+        plugin.bias_act(x, torch.randn(7, device=DEV), e, e, e, 0, 1, 3, 0.2, 1.0, -1.0)       # wrong bias length
+    with pytest.raises(RuntimeError):
+        plugin.bias_act(x.cpu(), b.cpu(), e, e, e, 0, 1, 3, 0.2, 1.0, -1.0)                    # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        plugin.bias_act(x[:, :, ::2], b, e, e, e, 0, 1, 3, 0.2, 1.0, -1.0)                     # not dense
+    with pytest.raises(RuntimeError):
+        custom_ops.get_plugin('filtered_lrelu_plugin', sources=[])
+    empty = torch.empty(0, 8, 5, 5, device=DEV)
+    assert bias_act.bias_act(empty, b, act='lrelu').shape == empty.shape                       # empty input
+
+
+@pytest.mark.parametrize('shape,cl', [((32, 64, 256, 256), True), ((32, 64, 256, 256), False), ((8, 512, 32, 32), True), ((3, 7, 33, 17), False)])
+def test_bias_act_full_size_properties(shape, cl):
+    """BASELINE.json sizes: compare with the same formula evaluated by torch elementwise ops on the device (an
+    independent code path), plus db == dx.sum, in fp16."""
+    torch.manual_seed(0)
+    x = torch.randn(shape, device=DEV, dtype=torch.float16)
+    b = torch.randn(shape[1], device=DEV, dtype=torch.float16)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    b.requires_grad_(True)
+    gain, clamp = float(np.sqrt(2)), 2.0
+    y = bias_act.bias_act(x, b, act='lrelu', gain=gain, clamp=clamp)
+    u = x.detach().float() + b.detach().float().reshape(1, -1, 1, 1)
+    ref = (torch.nn.functional.leaky_relu(u, 0.2) * gain).clamp(-clamp, clamp)
+    assert_close(y, ref.half(), 2e-3, 'y')
+    dy = torch.randn_like(y)
+    dx, db = torch.autograd.grad(y, [x, b], dy)
+    mask = (ref.abs() < clamp).float()
+    refdx = dy.float() * gain * torch.where(u > 0, 1.0, 0.2) * mask
+    # saturated elements sit exactly on the clamp after rounding; exclude the measure-zero boundary set
+    inner = ((y.detach().float().abs() - clamp).abs() > 1e-2)
+    assert_close(dx.float() * inner, refdx * inner, 2e-3, 'dx')
+    assert_close(db.float(), dx.float().sum([0, 2, 3]), 5e-3, 'db')
+
+
+# ---------------------------------------------------------------------------------------------------- upfirdn2d
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.float64])
+@pytest.mark.parametrize('cl', [False, True])
+@pytest.mark.parametrize('case', gg.UPFIRDN_CASES, ids=lambda c: c[0])
+def test_upfirdn2d_cases(golden, case, cl, dtype):
+    name, f, kw, shape = case
+    G = golden('ops_upfirdn2d.npz')
+    x = t(G[f'upfirdn2d/{name}/x'], dtype)
+    if cl:
+        # widen channels to a multiple of 8 so the channels-last vector kernel is the one exercised
+        reps = 8
+        x = x.repeat(1, reps, 1, 1).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    ft = upfirdn2d.setup_filter(f, device=DEV) if f is not None else None
+    y = upfirdn2d.upfirdn2d(x, ft, **kw)
+    yo = R.upfirdn2d(x.detach().float().cpu(), ft.cpu() if ft is not None else None, **kw)
+    assert y.shape == yo.shape
+    assert_close(y, yo, TOL[dtype] if dtype != torch.float64 else 1e-6, 'y')
+    if dtype == torch.float32 and not cl:
+        assert_close(y, G[f'upfirdn2d/{name}/y'], 1e-5, 'y vs golden')
+    dy = torch.randn_like(y)
+    dx, = torch.autograd.grad(y, x, dy)
+    xo = x.detach().float().cpu().requires_grad_(True)
+    dxo, = torch.autograd.grad(R.upfirdn2d(xo, ft.cpu() if ft is not None else None, **kw), xo, dy.float().cpu())
+    assert_close(dx, dxo, TOL[dtype] if dtype != torch.float64 else 1e-6, 'dx')
+    if cl:
+        assert y.is_contiguous(memory_format=torch.channels_last)
+
+
+def test_upfirdn2d_wrappers_strides_and_errors(golden):
+    G = golden('ops_upfirdn2d.npz')
+    x = t(G['upfirdn2d/wrappers/x'])
+    f4 = upfirdn2d.setup_filter(gg.F4, device=DEV)
+    assert_close(upfirdn2d.filter2d(x, f4), G['upfirdn2d/wrappers/filter2d'], 1e-5)
+    assert_close(upfirdn2d.upsample2d(x, f4), G['upfirdn2d/wrappers/upsample2d'], 1e-5)
+    assert_close(upfirdn2d.downsample2d(x[:, :, :, :6], f4), G['upfirdn2d/wrappers/downsample2d'], 1e-5)    # strided view input
+    # arbitrary strides: transposed view
+    xt = torch.randn(2, 3, 9, 7, device=DEV).transpose(2, 3)
+    assert_close(upfirdn2d.upfirdn2d(xt, f4, padding=1), R.upfirdn2d(xt.cpu(), f4.cpu(), padding=1), 1e-5)
+    # DC gain of upsample2d is 1 away from the border
+    ones = torch.ones(1, 1, 16, 16, device=DEV)
+    assert torch.allclose(upfirdn2d.upsample2d(ones, f4)[:, :, 3:-3, 3:-3], torch.ones(1, 1, 26, 26, device=DEV), atol=1e-6)
+    sym6 = upfirdn2d.setup_filter(gg.SYM6, device=DEV)
+    assert torch.allclose(upfirdn2d.upsample2d(ones, sym6)[:, :, 8:-8, 8:-8], torch.ones(1, 1, 16, 16, device=DEV), atol=1e-5)
+    plugin = custom_ops.get_plugin('upfirdn2d_plugin', sources=['upfirdn2d.cpp', 'upfirdn2d.cu'], headers=['upfirdn2d.h'], source_dir='.')
+    with pytest.raises(RuntimeError):
+        plugin.upfirdn2d(x, f4.double(), 1, 1, 1, 1, 0, 0, 0, 0, False, 1.0)         # f must be float32
+    with pytest.raises(RuntimeError):
+        plugin.upfirdn2d(x[:, :, :2, :2], f4, 1, 1, 1, 1, 0, 0, 0, 0, False, 1.0)    # output smaller than 1x1
+    with pytest.raises(RuntimeError):
+        plugin.upfirdn2d(x.cpu(), f4.cpu(), 1, 1, 1, 1, 0, 0, 0, 0, False, 1.0)      # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize('N,C,H,cl', [(8, 64, 257, True), (8, 64, 257, False), (4, 512, 33, True)])
+def test_upfirdn2d_full_size_vs_depthwise_conv(N, C, H, cl):
+    """G conv0's blur at full size: [N,C,2H+1,2H+1] -> [N,C,2H,2H], 4x4 taps, pad 1, gain 4; fp16.  Checked against a
+    depthwise torch convolution in fp32 (independent code path) and by linearity."""
+    torch.manual_seed(1)
+    x = torch.randn(N, C, H, H, device=DEV, dtype=torch.float16)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    f4 = upfirdn2d.setup_filter(gg.F4, device=DEV)
+    y = upfirdn2d.upfirdn2d(x, f4, padding=[1, 1, 1, 1], gain=4)
+    w = (f4.flip([0, 1]) * 4)[None, None].repeat(C, 1, 1, 1)
+    ref = torch.nn.functional.conv2d(x.float(), w, padding=1, groups=C)
+    assert y.shape == ref.shape
+    assert_close(y, ref, 2e-3, 'y')
+    y2 = upfirdn2d.upfirdn2d(x * 0.5, f4, padding=[1, 1, 1, 1], gain=4)
+    assert_close(y2.float() * 2, y.float(), 2e-3, 'linearity')
+
+
+# ---------------------------------------------------------------------------------------------------- conv family
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('case', gg.CONV_RESAMPLE_CASES, ids=lambda c: c[0])
+def test_conv2d_resample_cases(golden, case, dtype):
+    name, ci, co, k, kw, h = case
+    G = golden('ops_conv.npz')
+    x = t(G[f'conv2d_resample/{name}/x'], dtype).requires_grad_(True)
+    w = t(G[f'conv2d_resample/{name}/w'], dtype).requires_grad_(True)
+    dy = t(G[f'conv2d_resample/{name}/dy'], dtype)
+    f4 = upfirdn2d.setup_filter(gg.F4, device=DEV)
+    y = conv2d_resample.conv2d_resample(x, w, f=f4, **kw)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert_close(y, G[f'conv2d_resample/{name}/y'], tol, 'y')
+    dx, dw = torch.autograd.grad(y, [x, w], dy)
+    assert_close(dx, G[f'conv2d_resample/{name}/dx'], tol, 'dx')
+    assert_close(dw, G[f'conv2d_resample/{name}/dw'], tol, 'dw')
+
+
+@pytest.mark.parametrize('transpose,stride,pad', [(False, 1, 1), (False, 2, 0), (True, 2, 0), (False, 1, 0)])
+def test_conv_gradfix_double_backward(transpose, stride, pad):
+    """Second-order gradients of the conv Function family against torch's native double backward (fp64-free: fp32)."""
+    torch.manual_seed(2)
+    ci, co, k = 6, 5, 3
+    x = torch.randn(2, ci, 9, 9, device=DEV, requires_grad=True)
+    w = torch.randn((ci, co, k, k) if transpose else (co, ci, k, k), device=DEV, requires_grad=True)
+
+    def run(fn_conv, fn_convT):
+        y = (fn_convT if transpose else fn_conv)(x, w, stride=stride, padding=pad)
+        gy = torch.randn(y.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+        gx, gw = torch.autograd.grad(y, [x, w], gy, create_graph=True)
+        s = gx.square().sum() + (gw * gw.detach().sign()).sum()
+        ggx, ggw = torch.autograd.grad(s, [x, w])
+        return y, gx, gw, ggx, ggw
+
+    ours = run(conv2d_gradfix.conv2d, conv2d_gradfix.conv_transpose2d)
+    theirs = run(torch.nn.functional.conv2d, torch.nn.functional.conv_transpose2d)
+    for a, b, name in zip(ours, theirs, ['y', 'gx', 'gw', 'ggx', 'ggw']):
+        assert_close(a, b, 2e-5, name)
+    # no_weight_gradients() suppresses dw in first-order backward
+    y = conv2d_gradfix.conv2d(x, w if not transpose else w.transpose(0, 1).contiguous(), padding=1)
+    with conv2d_gradfix.no_weight_gradients():
+        gx, gw = torch.autograd.grad(y.sum(), [x, w], allow_unused=True)
+    assert gx is not None and gw is None
+
+
+def test_fma_and_grid_sample(golden):
+    G = golden('ops_conv.npz')
+    a, b, c = (t(G['fma/a']).requires_grad_(True), t(G['fma/b']).requires_grad_(True), t(G['fma/c']).requires_grad_(True))
+    y = fma.fma(a, b, c)
+    assert_close(y, G['fma/y'], 1e-6)
+    ga, gb, gc = torch.autograd.grad(y.sum(), [a, b, c])
+    assert ga.shape == a.shape and gb.shape == b.shape and gc.shape == c.shape
+    assert_close(gb, a.detach().sum([2, 3], keepdim=True), 1e-5)
+    img, grid = t(G['grid_sample/img']).requires_grad_(True), t(G['grid_sample/grid'])
+    out = grid_sample_gradfix.grid_sample(img, grid)
+    assert_close(out, G['grid_sample/y'], 1e-5)
+    g1, = torch.autograd.grad(out.square().sum(), img, create_graph=True)
+    g2, = torch.autograd.grad(g1.square().sum(), img)          # double backward must exist (R1 through the ADA pipe)
+    assert torch.isfinite(g2).all()
