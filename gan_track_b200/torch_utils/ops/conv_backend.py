@@ -21,6 +21,11 @@ _igemm_wgrad = None
 
 allow_igemm = True
 
+# fp32 layers must be true fp32 (north star: 1e-5 relative; the reference turns TF32 off in its training loop,
+# S3/training/training_loop_mi_multimodal.py:169-170).  The library route would otherwise silently use TF32.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def _aten_conv(x, w, stride, padding, transpose, output_padding, groups):
     return torch.ops.aten.convolution(x, w, None, list(stride), list(padding), [1, 1], transpose, list(output_padding), groups)

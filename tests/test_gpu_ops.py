@@ -106,7 +106,7 @@ def test_bias_act_all_activations(golden, act, dtype):
     b = t(G[f'bias_act_all/{act}/b'], dtype)
     dy = t(G[f'bias_act_all/{act}/dy'], dtype).requires_grad_(True)
     v = t(G[f'bias_act_all/{act}/v'], dtype)
-    tol = {torch.float32: 2e-5, torch.float64: 1e-9, torch.float16: 1e-2}[dtype]
+    tol = {torch.float32: 2e-5, torch.float64: 2e-7, torch.float16: 1e-2}[dtype]   # fp64: `gain` crosses the C ABI as a float, as in OPS/bias_act.cpp:32
     y = bias_act.bias_act(x, b, dim=1, act=act)
     assert_close(y, G[f'bias_act_all/{act}/y'], tol, 'y')
     dx, = torch.autograd.grad(y, x, dy, create_graph=True)
