@@ -54,3 +54,8 @@ def conv_wgrad(dy, x, weight_shape, *, transpose, output_padding, stride, paddin
     _, dw, _ = torch.ops.aten.convolution_backward(dy, x, w_dummy, None, list(stride), list(padding), [1, 1], transpose,
                                                    list(output_padding), groups, [False, True, False])
     return dw
+
+
+from . import conv_igemm  # noqa: E402  (registers the tcgen05 kernels as the first route)
+
+conv_igemm.install()

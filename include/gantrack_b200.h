@@ -71,6 +71,38 @@ int gt_upfirdn2d(const void* x, const float* f, void* y, int dtype, int N, int C
                  int OW, long long ys_n, long long ys_c, long long ys_h, long long ys_w, int upx, int upy, int downx,
                  int downy, int padx0, int pady0, int flip, float gain, void* stream);
 
+/* ---- convolution (fp16, NHWC, tcgen05 implicit GEMM) ------------------------------------------------------------
+ * New relative to the reference, which delegates every convolution to cuDNN through torch.nn.functional.conv2d /
+ * conv_transpose2d (OPS/conv2d_gradfix.py:37-45).  One entry point covers the forward and data-gradient convolutions of
+ * the StyleGAN2 path (OPS/conv2d_resample.py:94-134): stride 1 (any pad < 8), stride 2, transposed stride 1, and
+ * transposed stride 2 with pad 0; kernels up to 9 taps.  Cin and Cout must be multiples of 64, groups = 1.
+ *   x: [N,H,W,Cin] fp16, channel stride 1, other strides (elements, multiples of 8) xs_n / xs_h / xs_w.
+ *   y: [N,OH,OW,Cout] fp16, channel stride 1, strides ys_*; the caller computes OH / OW exactly as torch does.
+ *   wpacked: [KH*KW][Cout][Cin] fp16 contiguous, produced by gt_conv_pack_weight_f16 from a weight tensor with
+ *   arbitrary element strides: wpacked[r*KW+s][co][ci] = w[co*s_co + ci*s_ci + r*s_r + s*s_s].  For a transposed
+ *   convolution (torch weight layout [Cin,Cout,KH,KW]) pass s_co = stride of dim 1 and s_ci = stride of dim 0.
+ * transposed = 0: y[n,oy,ox,co] = sum x[n, oy*stride + r - pad, ox*stride + s - pad, ci] * w[co,ci,r,s]   (correlation)
+ * transposed = 1: y[n, i*stride + r - pad, j*stride + s - pad, co] += x[n,i,j,ci] * w[ci,co,r,s]. */
+int gt_conv_pack_weight_f16(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin,
+                            int KH, int KW, void* wpacked, void* stream);
+int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y,
+                        long long ys_n, long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                        int KH, int KW, int stride, int pad, int transposed, void* stream);
+
+/* Weight gradient of the same convolutions (replaces cuDNN wgrad reached through autograd of F.conv2d /
+ * F.conv_transpose2d, OPS/conv2d_gradfix.py:37-45).  U is the operand walked pixel by pixel, S the operand read at
+ * shifted / strided positions:
+ *     dw[u_ch][s_ch][r][c] = sum_{n,i,j} U[n,i,j,u_ch] * S[n, i*stride + r - pad, j*stride + c - pad, s_ch]
+ * conv2d: U = dy, S = x (dw is [Cout,Cin,KH,KW]); conv_transpose2d: U = x, S = dy (dw is [Cin,Cout,KH,KW]).
+ * U: [N,UH,UW,UC] fp16 NHWC with strides us_*; S: [N,SH,SW,SC] likewise.  dw: fp16, element strides ds_u / ds_s /
+ * ds_r / ds_c.  Split-K partial sums go through `workspace` (fp32, at least gt_conv2d_wgrad_workspace(...) floats) and
+ * are reduced in a fixed order, so the result is deterministic. */
+long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW);
+int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s,
+                        long long ss_n, long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride,
+                        int pad, void* dw, long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace,
+                        long long workspace_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
