@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-overlap', action='store_true')
     ap.add_argument('--cpu-batch', type=int, default=4)
+    ap.add_argument('--profile-range', action='store_true', help='cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)')
     return ap.parse_args()
 
 
@@ -269,11 +270,15 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.profiler.start()
     s.record()
     for _ in range(args.steps):
         trainer.train_step(dev_img, dev_c)
     e.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(s.elapsed_time(e))
     launches = _lib.launches - launches0

@@ -48,6 +48,15 @@ def test_sass_is_sm100a(lib_path):
     assert 'sm_100a' in out, out[:500]
 
 
+def test_conv_kernels_are_tcgen05_tma(lib_path):
+    """The convolution objects carry Blackwell tensor-core / TMA / TMEM SASS (UTCHMMA, UTMALDG, LDTM), not HMMA."""
+    from gan_track_b200 import build
+    for obj in ('conv_igemm.o', 'conv_wgrad.o'):
+        sass = subprocess.run(['cuobjdump', '-sass', os.path.join(build.OBJ, obj)], capture_output=True, text=True).stdout
+        assert 'UTCHMMA' in sass and 'UTMALDG' in sass and 'LDTM' in sass, obj
+        assert 'HMMA.16' not in sass
+
+
 def test_product_ops_refuse_cpu_tensors():
     import torch
     from gan_track_b200.torch_utils.ops import bias_act, conv2d_gradfix, upfirdn2d

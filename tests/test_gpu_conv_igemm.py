@@ -1,0 +1,112 @@
+"""GPU: the tcgen05 implicit-GEMM convolutions (csrc/conv_igemm.cu, csrc/conv_wgrad.cu) through the C ABI against the
+arithmetic the reference runs -- torch's own convolution (OPS/conv2d_gradfix.py:40,45) -- evaluated in fp32 on the same
+fp16 inputs.  Tolerance: fp16 layers within 1e-2 relative (north star); observed <= 5e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-3   # well inside the 1e-2 the north star allows for fp16 layers
+
+# (name, N, Cin, Cout, H, W, k, stride, pad, transpose) -- every conv flavour on the StyleGAN2 path and
+# its data gradient, ragged sizes (33, 257 = 2H+1 of the up path), tiny maps (4x4, 8x8: several images per tile).
+CASES = [
+    ('3x3_p1_64_64_32', 2, 64, 64, 32, 32, 3, 1, 1, False),
+    ('3x3_p1_128_256_16', 4, 128, 256, 16, 16, 3, 1, 1, False),
+    ('3x3_p1_64_128_33', 3, 64, 128, 33, 33, 3, 1, 1, False),
+    ('3x3_p1_64_64_8', 8, 64, 64, 8, 8, 3, 1, 1, False),
+    ('3x3_p1_64_64_4', 5, 64, 64, 4, 4, 3, 1, 1, False),
+    ('3x3_p1_512_512_32', 2, 512, 512, 32, 32, 3, 1, 1, False),
+    ('1x1_128_64_32', 2, 128, 64, 32, 32, 1, 1, 0, False),
+    ('3x3_s2_64_128_33', 2, 64, 128, 33, 33, 3, 2, 0, False),
+    ('3x3_s2_64_64_257', 1, 64, 64, 257, 257, 3, 2, 0, False),
+    ('3x3_T_s2_128_64_16', 2, 128, 64, 16, 16, 3, 2, 0, True),
+    ('3x3_T_s2_64_64_128', 1, 64, 64, 128, 128, 3, 2, 0, True),
+    ('3x3_T_s1_p1_64_128_32', 2, 64, 128, 32, 32, 3, 1, 1, True),
+    ('3x3_T_s1_p0_64_64_16', 2, 64, 64, 16, 16, 3, 1, 0, True),
+]
+
+
+def _inputs(N, ci, co, H, W, k, tr, seed=0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    x = torch.randn([N, ci, H, W], device='cuda', generator=g).to(torch.float16).contiguous(memory_format=torch.channels_last)
+    wshape = [ci, co, k, k] if tr else [co, ci, k, k]
+    w = (torch.randn(wshape, device='cuda', generator=g) / (ci * k * k) ** 0.5).to(torch.float16)
+    return x, w
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: c[0])
+def test_igemm_forward_matches_torch(case):
+    from gan_track_b200.torch_utils.ops import conv_igemm
+    _, N, ci, co, H, W, k, s, p, tr = case
+    x, w = _inputs(N, ci, co, H, W, k, tr)
+    y = conv_igemm.igemm_forward(x, w, transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
+    assert y is not None, 'case must be covered by the tcgen05 kernel'
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv_transpose2d(x.float(), w.float(), stride=s, padding=p) if tr else F.conv2d(x.float(), w.float(), stride=s, padding=p)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert y.shape == ref.shape and y.dtype == torch.float16
+    assert _rel(y, ref) <= TOL
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: c[0])
+def test_igemm_wgrad_matches_torch(case):
+    from gan_track_b200.torch_utils.ops import conv_igemm
+    _, N, ci, co, H, W, k, s, p, tr = case
+    x, w = _inputs(N, ci, co, H, W, k, tr, seed=1)
+    OH, OW = conv_igemm.out_size(H, W, k, k, s, p, tr)
+    dy = torch.randn([N, co, OH, OW], device='cuda').to(torch.float16).contiguous(memory_format=torch.channels_last)
+    dw = conv_igemm.igemm_wgrad(dy, x, tuple(w.shape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
+    assert dw is not None
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        _, ref, _ = torch.ops.aten.convolution_backward(dy.float(), x.float(), w.float(), None, [s, s], [p, p], [1, 1], tr, [0, 0], 1,
+                                                        [False, True, False])
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert dw.shape == ref.shape
+    assert _rel(dw, ref) <= TOL
+    # deterministic: the split-K reduction has a fixed order
+    dw2 = conv_igemm.igemm_wgrad(dy, x, tuple(w.shape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
+    assert torch.equal(dw, dw2)
+
+
+def test_igemm_linearity_and_adjointness_full_size():
+    """Size-independent properties at a training shape: conv is linear in x, and <conv(x), dy> == <x, dgrad(dy)> == <w, wgrad>."""
+    from gan_track_b200.torch_utils.ops import conv_igemm
+    N, ci, co, H = 8, 128, 128, 128
+    x, w = _inputs(N, ci, co, H, H, 3, False, seed=2)
+    kw = dict(output_padding=(0, 0), stride=(1, 1), padding=(1, 1), groups=1)
+    y = conv_igemm.igemm_forward(x, w, transpose=False, **kw).float()
+    y2 = conv_igemm.igemm_forward(x * 0.5, w, transpose=False, **kw).float()          # power-of-two scaling is exact in fp16
+    assert _rel(y2 * 2, y) <= 1e-3
+    dy = torch.randn_like(y).to(torch.float16).contiguous(memory_format=torch.channels_last)
+    dx = conv_igemm.igemm_forward(dy, w, transpose=True, **kw).float()
+    dw = conv_igemm.igemm_wgrad(dy, x, tuple(w.shape), transpose=False, **kw).float()
+    a = float((y.double() * dy.double()).sum())
+    b = float((x.double() * dx.double()).sum())
+    c = float((w.double() * dw.double()).sum())
+    scale = float(y.double().norm() * dy.double().norm())
+    assert abs(a - b) <= 2e-3 * scale and abs(a - c) <= 2e-3 * scale
+
+
+def test_conv_backend_routes_fp16_path_shapes_to_igemm():
+    from gan_track_b200.torch_utils.ops import conv2d_gradfix, conv_backend
+    x, w = _inputs(2, 64, 64, 32, 32, 3, False)
+    before = dict(conv_backend.stats)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y = conv2d_gradfix.conv2d(x, w, padding=1)
+    y.sum().backward()
+    assert conv_backend.stats['igemm'] - before['igemm'] == 2            # forward + dgrad
+    assert conv_backend.stats['igemm_wgrad'] - before['igemm_wgrad'] == 1
+    assert conv_backend.stats['library'] == before['library']

@@ -1,0 +1,40 @@
+"""The hot kernels at their training shapes (batch 32, 256x256 config), a few launches each -- the command the
+`ncu --set full` captures under profiles/ are taken on.  Usage: python tools/ncu_targets.py [--reps 2]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from gan_track_b200.torch_utils.ops import bias_act, conv_igemm, upfirdn2d  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--reps', type=int, default=2)
+a = ap.parse_args()
+dev = torch.device('cuda', 0)
+torch.manual_seed(0)
+cl = torch.channels_last
+
+
+def t(shape):
+    return torch.randn(shape, device=dev).to(torch.float16).contiguous(memory_format=cl)
+
+
+cfg = dict(output_padding=(0, 0), groups=1)
+x256 = t([32, 256, 64, 64]); w256 = t([256, 256, 3, 3]) * 0.02            # G b64 conv1 / D b64 conv0
+x64 = t([32, 64, 256, 256]); w64 = t([64, 64, 3, 3]) * 0.04               # G b256 conv1 / D b256 conv0
+x128 = t([32, 128, 128, 128]); wT = t([128, 64, 3, 3]) * 0.03             # G b256 conv0 (transposed stride 2)
+xb = t([32, 64, 257, 257])
+f = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
+b = torch.randn([64], device=dev, dtype=torch.float16)
+for _ in range(a.reps):
+    conv_igemm.igemm_forward(x256, w256, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    conv_igemm.igemm_forward(x64, w64, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    conv_igemm.igemm_forward(x128, wT, transpose=True, stride=(2, 2), padding=(0, 0), **cfg)
+    conv_igemm.igemm_wgrad(x256, x256, (256, 256, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    conv_igemm.igemm_wgrad(x64, x64, (64, 64, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    upfirdn2d.upfirdn2d(xb, f, padding=[1, 1, 1, 1], gain=4)
+    bias_act.bias_act(x64, b, act='lrelu', clamp=256.0)
+torch.cuda.synchronize()
+print('ok')
