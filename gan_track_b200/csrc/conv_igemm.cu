@@ -22,8 +22,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warps 2-5 = epilogue
 // (TMEM -> registers -> fp16 -> global, one output pixel per thread, 64 contiguous bytes per tcgen05.ld chunk).
 // smem ring of STAGES {A 16 KB, B BN*128 B} guarded by full/empty mbarriers; tcgen05.commit releases a stage.
-#include "gt_common.cuh"
-#include "gt_sm100.cuh"
+#include "conv_common.cuh"
 
 using namespace sm100;
 
@@ -42,28 +41,8 @@ namespace {
 
 constexpr int BM = 128;   // output pixels per tile (UMMA M)
 constexpr int BK = 64;    // channels per k-block
-constexpr int MAX_TAPS = 9;
-constexpr int MAX_PHASES = 4;
+constexpr int MAX_TAPS = CONV_MAX_TAPS;
 constexpr int NTHREADS = 192;
-
-struct ConvPhase {
-    int ntaps;
-    int OHp, OWp;        // extent of this phase's output grid
-    int off_y, off_x;    // output pixel = (a * out_stride + off_y, b * out_stride + off_x)
-    int8_t tdy[MAX_TAPS], tdx[MAX_TAPS], tw[MAX_TAPS];   // input offset of the tap, weight slab of the tap
-};
-
-struct ConvParams {
-    ConvPhase ph[MAX_PHASES];
-    int nphases;
-    int N, Cin, Cout;
-    int in_stride, out_stride;
-    int bw_log2, bh_log2;            // tile box bw x bh x bn pixels, product 128
-    int tiles_w, tiles_h, tiles_n;   // over the largest phase
-    int n_tiles;                     // Cout / BN
-    __half* y;
-    long long ys_n, ys_h, ys_w;
-};
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -252,6 +231,21 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
 
 }  // namespace
 
+extern int g_conv_halo_tuning;
+static int g_conv_variant = 0;   // 0 = auto (halo kernel where applicable), 1 = per-tap kernel only
+
+extern "C" int gt_conv_igemm_config(int variant) {
+    const int old = g_conv_variant;
+    if (variant == 0 || variant == 1) {
+        g_conv_variant = variant;
+        g_conv_halo_tuning = 0;
+    } else if (variant >= 2) {   // halo kernel with an alternative tile choice (tuning experiments)
+        g_conv_variant = 0;
+        g_conv_halo_tuning = variant;
+    }
+    return old;
+}
+
 extern "C" int gt_conv_pack_weight_f16(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin, int KH, int KW,
                                        void* out, void* stream) {
     GT_REQUIRE(w && out, "gt_conv_pack_weight_f16: null pointer");
@@ -358,6 +352,9 @@ extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h
     p.tiles_w = (maxOW + bw - 1) / bw;
     p.tiles_h = (maxOH + bh - 1) / bh;
     p.tiles_n = (N + bn - 1) / bn;
+
+    if (g_conv_variant != 1 && p.in_stride == 1 && gt_conv_halo_applicable(p, maxOH, maxOW))
+        return gt_launch_conv_halo(x, xs_n, xs_h, xs_w, H, W, wpacked, KH * KW, p, (cudaStream_t)stream);
 
     gt_encode_tiled_fn encode = gt_get_encode_tiled();
     GT_REQUIRE(encode != nullptr, "gt_conv2d_igemm_f16: cuTensorMapEncodeTiled is not available from this driver");

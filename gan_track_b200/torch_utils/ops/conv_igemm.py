@@ -60,7 +60,7 @@ def pack_weight(w, transpose):
     return packed
 
 
-def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups):
+def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, packed=None):
     if not covered(x, w, transpose, output_padding, stride, padding, groups):
         return None
     lib = _lib.load()
@@ -72,7 +72,8 @@ def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups):
     if OH <= 0 or OW <= 0:
         return None
     with torch.cuda.device(x.device):
-        packed = pack_weight(w, transpose)
+        if packed is None:
+            packed = pack_weight(w, transpose)
         y = torch.empty([N, cout, OH, OW], dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
         ys_n, ys_h, ys_w = OH * OW * cout, OW * cout, cout
         _lib.check(lib.gt_conv2d_igemm_f16(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,

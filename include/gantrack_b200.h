@@ -83,6 +83,9 @@ int gt_upfirdn2d(const void* x, const float* f, void* y, int dtype, int N, int C
  *   convolution (torch weight layout [Cin,Cout,KH,KW]) pass s_co = stride of dim 1 and s_ci = stride of dim 0.
  * transposed = 0: y[n,oy,ox,co] = sum x[n, oy*stride + r - pad, ox*stride + s - pad, ci] * w[co,ci,r,s]   (correlation)
  * transposed = 1: y[n, i*stride + r - pad, j*stride + s - pad, co] += x[n,i,j,ci] * w[ci,co,r,s]. */
+/* Kernel selection for gt_conv2d_igemm_f16: 0 = automatic (halo-staged persistent kernel where it applies, per-tap kernel
+ * otherwise), 1 = per-tap kernel only.  A negative value only queries.  Returns the previous setting. */
+int gt_conv_igemm_config(int variant);
 int gt_conv_pack_weight_f16(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin,
                             int KH, int KW, void* wpacked, void* stream);
 int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y,

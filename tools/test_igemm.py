@@ -15,8 +15,11 @@ from gan_track_b200.torch_utils.ops import conv_igemm  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--time', action='store_true')
 ap.add_argument('--wgrad', action='store_true')
+ap.add_argument('--variant', type=int, default=0)
 args = ap.parse_args()
 dev = torch.device('cuda', 0)
+from gan_track_b200 import _lib  # noqa: E402
+_lib.load().gt_conv_igemm_config(args.variant)
 torch.manual_seed(0)
 torch.backends.cudnn.benchmark = True
 
@@ -35,6 +38,12 @@ CASES = [
     ('3x3 T s2 64->64 128x128', 1, 64, 64, 128, 128, 3, 2, 0, True),
     ('3x3 T s1 p1 64->128 32x32', 2, 64, 128, 32, 32, 3, 1, 1, True),
     ('3x3 T s1 p0 64->64 16x16', 2, 64, 64, 16, 16, 3, 1, 0, True),
+    ('3x3 p1 64->64 64x64', 2, 64, 64, 64, 64, 3, 1, 1, False),
+    ('3x3 p1 128->128 40x72', 3, 128, 128, 40, 72, 3, 1, 1, False),
+    ('3x3 p1 256->512 32x32', 2, 256, 512, 32, 32, 3, 1, 1, False),
+    ('1x1 128->256 64x64', 2, 128, 256, 64, 64, 1, 1, 0, False),
+    ('3x3 T s2 128->64 32x32', 2, 128, 64, 32, 32, 3, 2, 0, True),
+    ('3x3 T s2 256->128 64x64', 1, 256, 128, 64, 64, 3, 2, 0, True),
 ]
 
 
@@ -128,12 +137,20 @@ if args.time and fails == 0:
         w = (torch.randn(wshape, device=dev) / (ci * k * k) ** 0.5).to(torch.float16).contiguous(memory_format=torch.channels_last)
         OH, OW = conv_igemm.out_size(H, W, k, k, s, p, tr)
         flops = 2.0 * N * ci * co * k * k * (H * W if tr else OH * OW)
-        t_ours = bench(lambda: conv_igemm.igemm_forward(x, w, transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1))
+        pk = conv_igemm.pack_weight(w, tr)
+        kw_ = dict(transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
+        t_full = bench(lambda: conv_igemm.igemm_forward(x, w, **kw_))
+        res = {}
+        for v in (0, 2, 3, 1):
+            _lib.load().gt_conv_igemm_config(v)
+            res[v] = bench(lambda: conv_igemm.igemm_forward(x, w, packed=pk, **kw_))
+        _lib.load().gt_conv_igemm_config(args.variant)
+        t_ours, t_v2, t_v3, t_v1 = res[0], res[2], res[3], res[1]
         if tr:
             t_lib = bench(lambda: F.conv_transpose2d(x, w, stride=s, padding=p))
         else:
             t_lib = bench(lambda: F.conv2d(x, w, stride=s, padding=p))
-        line = f'{name:40s} fwd ours {t_ours * 1e3:7.1f} us {flops / t_ours / 1e9:6.0f} TF/s | cudnn {t_lib * 1e3:7.1f} us {flops / t_lib / 1e9:6.0f} TF/s'
+        line = f'{name:40s} fwd ours {t_ours * 1e3:7.1f} us {flops / t_ours / 1e9:6.0f} TF/s (+pack {t_full * 1e3:6.1f}; per-tap {t_v1 * 1e3:6.1f}, cfg2 {t_v2 * 1e3:6.1f}, cfg3 {t_v3 * 1e3:6.1f}) | cudnn {t_lib * 1e3:7.1f} us {flops / t_lib / 1e9:6.0f} TF/s'
         if args.wgrad:
             dy = torch.randn([N, co, OH, OW], device=dev).to(torch.float16).contiguous(memory_format=torch.channels_last)
             t_w = bench(lambda: conv_igemm.igemm_wgrad(dy, x, tuple(wshape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1))
