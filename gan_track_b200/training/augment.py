@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..torch_utils import misc
-from ..torch_utils.ops import conv2d_gradfix, grid_sample_gradfix, upfirdn2d
+from ..torch_utils.ops import aug_warp, conv2d_gradfix, grid_sample_gradfix, upfirdn2d
 
 # Low-pass decomposition filters (orthogonal wavelets); the pipe uses sym6 for resampling and sym2 for the band filter.
 wavelets = {
@@ -106,6 +106,8 @@ class AugmentPipe(torch.nn.Module):
         self.noise, self.cutout, self.noise_std, self.cutout_size = float(noise), float(cutout), float(noise_std), float(cutout_size)
 
         self.register_buffer('Hz_geom', upfirdn2d.setup_filter(wavelets['sym6']))
+        self._hz_geom_taps = tuple(float(v) for v in self.Hz_geom.tolist())     # host copy for the fused warp kernel
+        self.fused_warp = True      # False: the reference's op-by-op sequence with the host read of the margins
 
         # Band-pass bank for the image-space filter: H(z) = sym2 low-pass, dyadic cascade of 4 bands.
         lo = np.asarray(wavelets['sym2'])
@@ -293,6 +295,20 @@ class AugmentPipe(torch.nn.Module):
         m = m + misc.constant([Hz_pad * 2 - cx, Hz_pad * 2 - cy] * 2, device=dev)
         m = m.max(misc.constant([0, 0] * 2, device=dev))
         m = m.min(misc.constant([W - 1, H - 1] * 2, device=dev))
+        if self.fused_warp and images.is_cuda and images.dtype == torch.float32:
+            # Margins stay on the device; pad + upsample + affine resampling run as one gather kernel.
+            mf = m.ceil()
+            G_inv = translate2d((mf[0] - mf[2]) / 2, (mf[1] - mf[3]) / 2, device=dev) @ G_inv
+            G_inv = scale2d(2, 2, device=dev) @ G_inv @ scale2d_inv(2, 2, device=dev)
+            G_inv = translate2d(-0.5, -0.5, device=dev) @ G_inv @ translate2d_inv(-0.5, -0.5, device=dev)
+            wu = (mf[0] + mf[2] + W) * 2
+            hu = (mf[1] + mf[3] + H) * 2
+            shape = [B, C, (H + Hz_pad * 2) * 2, (W + Hz_pad * 2) * 2]
+            G_inv = scale2d(2 / wu, 2 / hu, device=dev) @ G_inv @ scale2d_inv(2 / shape[3], 2 / shape[2], device=dev)
+            theta = G_inv[:, :2, :].to(torch.float32).contiguous()
+            images = aug_warp.warp(images, theta, mf.to(torch.int32).contiguous(), self._hz_geom_taps, shape[2:])
+            return upfirdn2d.downsample2d(x=images, f=self.Hz_geom, down=2, padding=-Hz_pad * 2, flip_filter=True)
+
         mx0, my0, mx1, my1 = (int(v) for v in m.ceil().to(torch.int32).tolist())                # one device->host sync
 
         images = torch.nn.functional.pad(input=images, pad=[mx0, mx1, my0, my1], mode='reflect')

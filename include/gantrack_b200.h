@@ -106,6 +106,17 @@ int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long
                         int pad, void* dw, long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace,
                         long long workspace_floats, void* stream);
 
+/* ---- ADA geometric warp (fp32) ------------------------------------------------------------------------------------
+ * One gather kernel for S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps, up=2)
+ * -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE
+ * int[4] (mx0, my0, mx1, my1), so the host never reads it back (the reference syncs at :299).  `taps_host` is a HOST
+ * array of ntaps normalised low-pass taps (even, <= 12; sym6 on the path).  x: [B,C,H,W], y: [B,C,OH,OW], theta: [B,2,3].
+ * gt_aug_warp_bwd is the adjoint (gx is zeroed, then accumulated with atomicAdd). */
+int gt_aug_warp_fwd(const float* x, const float* theta, const int* margins, const float* taps_host, int ntaps, float* y, int B,
+                    int C, int H, int W, int OH, int OW, void* stream);
+int gt_aug_warp_bwd(const float* gy, const float* theta, const int* margins, const float* taps_host, int ntaps, float* gx, int B,
+                    int C, int H, int W, int OH, int OW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
