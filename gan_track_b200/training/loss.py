@@ -46,7 +46,12 @@ class StyleGAN2Loss(Loss):
         if self.style_mixing_prob > 0:
             cutoff = torch.empty([], dtype=torch.int64, device=ws.device).random_(1, ws.shape[1])
             cutoff = torch.where(torch.rand([], device=ws.device) < self.style_mixing_prob, cutoff, torch.full_like(cutoff, ws.shape[1]))
-            ws[:, cutoff:] = self.G.mapping(torch.randn_like(z), c, update_emas=False)[:, cutoff:]
+            # ws[:, cutoff:] = mapping(z2)[:, cutoff:] of the reference (S3/training/loss.py:48), written as a select so that
+            # the random cutoff never leaves the device (slicing with a tensor index is a host sync, which would also make the
+            # phase impossible to capture in a CUDA graph); same random draws in the same order
+            ws2 = self.G.mapping(torch.randn_like(z), c, update_emas=False)
+            layer = torch.arange(ws.shape[1], device=ws.device).reshape(1, -1, 1)
+            ws = torch.where(layer < cutoff, ws, ws2)
         img = self.G.synthesis(ws, update_emas=update_emas)
         return img, ws
 

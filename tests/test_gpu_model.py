@@ -144,3 +144,25 @@ def test_augment_pipe_cuda_known_answers(golden):
     for pct in ref_pipe_keys:
         out = pipe(x, False, debug_percentile=pct)
         assert torch.isfinite(out).all()
+
+
+def test_trainer_cuda_graph_mode_runs_and_captures():
+    """Graph mode: every phase is captured at its second occurrence and replayed; parameters stay finite and move."""
+    from gan_track_b200.training import training_loop as tl
+    cfg = tl.claro_config(resolution=32, batch=4, num_gpus=1, cbase=1024, cmax=64, map_depth=2)
+    trainer = tl.Trainer(cfg, rank=0, device='cuda', use_graphs=True)
+    real = torch.rand(4, 1, 32, 32) * 255
+    c = torch.nn.functional.one_hot(torch.tensor([0, 1, 1, 0]), 2).float()
+    before = [p.detach().clone() for p in trainer.G.parameters()]
+    for _ in range(18):
+        trainer.train_step(real, c)
+    torch.cuda.synchronize()
+    assert all(ph.graphs is not None for ph in trainer.phases), 'Gmain/Greg/Dmain/Dreg must all be captured after 17 iterations'
+    assert trainer.phase_counts == {'Gmain': 18, 'Greg': 5, 'Dmain': 18, 'Dreg': 2}
+    moved = 0
+    for p, b in zip(trainer.G.parameters(), before):
+        assert torch.isfinite(p).all()
+        moved += int(not torch.equal(p, b))
+    assert moved > 0
+    for p in trainer.D.parameters():
+        assert torch.isfinite(p).all()

@@ -18,14 +18,15 @@ ap.add_argument('--batch', type=int, default=32)
 ap.add_argument('--res', type=int, default=256)
 ap.add_argument('--out', default='gpurun_out/step_profile.txt')
 ap.add_argument('--aug', default='ada')
+ap.add_argument('--graphs', action='store_true')
 a = ap.parse_args()
 
 dev = torch.device('cuda', 0)
 cfg = tl.claro_config(resolution=a.res, batch=a.batch, aug=a.aug)
-tr = tl.Trainer(cfg, device=dev)
+tr = tl.Trainer(cfg, device=dev, use_graphs=a.graphs)
 img = torch.rand([a.batch, 1, a.res, a.res], device=dev) * 255
 c = torch.nn.functional.one_hot(torch.randint(0, 2, [a.batch]), 2).float().to(dev)
-for _ in range(3):
+for _ in range(17 if a.graphs else 3):
     tr.train_step(img, c)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
