@@ -42,7 +42,9 @@ with open(a.out, 'w') as f:
     f.write(f'steps={a.steps} batch={a.batch} res={a.res} wall_ms_per_step={wall / a.steps * 1e3:.2f} gpu_busy_ms_per_step={total / a.steps / 1e3:.2f} '
             f'kernels_per_step={sum(r.count for r in rows) / a.steps:.0f}\n')
     f.write(f'{"share":>6} {"ms/step":>9} {"calls/step":>10} {"us/call":>9}  name\n')
-    for r in rows[:70]:
+    small = [r for r in rows if r.device_time_total / max(r.count, 1) < 6.0]
+    f.write(f'# kernels averaging < 6 us: {sum(r.count for r in small) / a.steps:.0f} launches/step, {sum(r.device_time_total for r in small) / a.steps / 1e3:.2f} ms/step\n')
+    for r in rows[:110]:
         f.write(f'{r.device_time_total / total * 100:6.2f} {r.device_time_total / a.steps / 1e3:9.3f} {r.count / a.steps:10.1f} '
                 f'{r.device_time_total / max(r.count, 1):9.1f}  {r.key[:150]}\n')
 print(open(a.out).read()[:6000])
