@@ -1,0 +1,351 @@
+// modulated.cu -- the element-wise halves of the training-mode modulated convolution on channels-last tensors, fused.
+//
+// Reference (S3/training/networks_stylegan2.py:68-77 and :325-327, S3 = /root/reference/src/models/stylegan3):
+//     x = x * styles.to(x.dtype)[:, :, None, None]                       one full pass (+ 3 in backward)
+//     x = conv2d_resample(x, w, ...)
+//     x = fma(x, dcoefs.to(x.dtype)[:, :, None, None], noise)            one full pass (+ 3-4 in backward, OPS/fma.py:15-58)
+//     x = bias_act(x, b, act, gain, clamp)                                one full pass (+ 1 in backward + db reduction)
+// Here:
+//     gt_mod_scale_fwd        y = x * s[n,c]
+//     gt_mod_scale_bwd        gx = gy * s[n,c]   and   gs[n,c] = sum_hw gy * x          one pass, deterministic reduction
+//     gt_demod_act_fwd        y = clamp(act(x * d[n,c] + noise[n,hw] + b[c]) * gain)     one pass
+//     gt_demod_act_bwd        g1 = gy * gain * act'(y) * [|y| < clamp];  gx = g1 * d[n,c];
+//                             gd[n,c] = sum_hw g1 * x;  s0[n,c] = sum_hw g1 (-> db);  gnoise[n,hw] = sum_c g1      one pass
+// All tensors are [N, P, C] (P = H*W pixels, C contiguous, C % (16 / sizeof(T)) == 0); s, d, gs, gd, s0 are fp32 [N,C].
+// Math is fp32 for fp16 I/O (as OPS/bias_act.cu:15-18).  act: 1 = linear, 3 = lrelu (the two on the StyleGAN2 path).
+// Reductions over pixels: a CTA owns (n, band of pixels); per-CTA partials go to a workspace and are summed in band
+// order by a second kernel, so results are bit-reproducible.
+#include "gt_common.cuh"
+
+namespace {
+
+constexpr int A_LINEAR = 1, A_LRELU = 3;
+constexpr int MAXJ = 4;   // channel-vector chunks per thread: C <= 32 lanes * MAXJ * VEC
+
+template <class T>
+__global__ void __launch_bounds__(256) mod_scale_fwd_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y, int C, long long P,
+                                                            long long total_vecs) {
+    constexpr int VEC = Vec16<T>::N;
+    const int cvecs = C / VEC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvecs);
+        const long long n = (i / cvecs) / P;
+        const Vec16<T> v = ld16_stream(x + i * VEC);
+        const float* sp = s + n * C + cv * VEC;
+        Vec16<T> o;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) o.v[k] = from_acc<T>((float)to_acc<T>(v.v[k]) * (float)to_acc<T>(from_acc<T>(sp[k])));
+        st16_stream(y + i * VEC, o);
+    }
+}
+
+// Shared structure of the two backward kernels: grid = (bands, N); lanes = min(cvecs, 32) threads cover the channel
+// vectors of one pixel (each thread owns cv = lane + lanes * j), 256 / lanes pixel rows are in flight per CTA.
+struct BandGeom {
+    int cvecs, lanes, nj, rgroups, rg, lane;
+};
+template <int VEC>
+__device__ __forceinline__ BandGeom band_geom(int C) {
+    BandGeom g;
+    g.cvecs = C / VEC;
+    g.lanes = g.cvecs < 32 ? g.cvecs : 32;
+    g.nj = (g.cvecs + g.lanes - 1) / g.lanes;
+    g.rgroups = 256 / g.lanes;
+    g.rg = threadIdx.x / g.lanes;
+    g.lane = threadIdx.x - g.rg * g.lanes;
+    return g;
+}
+
+// Combine the per-thread accumulators of the row groups in a fixed order and write this CTA's partial [C] vector.
+template <int VEC>
+__device__ __forceinline__ void write_partial(const BandGeom& g, float (&acc)[MAXJ][VEC], float* red, float* __restrict__ out, int C) {
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++) {
+        if (j < g.nj) {   // uniform across the CTA
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < VEC; k++) red[threadIdx.x * VEC + k] = acc[j][k];
+            __syncthreads();
+            const int cv = g.lane + g.lanes * j;
+            if (g.rg == 0 && cv < g.cvecs) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    float sum = 0.f;
+                    for (int r = 0; r < g.rgroups; r++) sum += red[(r * g.lanes + g.lane) * VEC + k];
+                    out[cv * VEC + k] = sum;
+                }
+            }
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) mod_scale_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const float* __restrict__ s,
+                                                            T* __restrict__ gx, float* __restrict__ partial, int C, long long P) {
+    constexpr int VEC = Vec16<T>::N;
+    __shared__ float red[256 * VEC];
+    const BandGeom g = band_geom<VEC>(C);
+    const int band = blockIdx.x, bands = gridDim.x, n = blockIdx.y;
+    float acc[MAXJ][VEC];
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[j][k] = 0.f;
+    const long long base = (long long)n * P * C;
+    for (long long p = band + (long long)bands * g.rg; p < P; p += (long long)bands * g.rgroups) {
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++) {
+            const int cv = g.lane + g.lanes * j;
+            if (j < g.nj && cv < g.cvecs) {
+                const long long e = base + p * C + (long long)cv * VEC;
+                const Vec16<T> gv = ld16_stream(gy + e), xv = ld16_stream(x + e);
+                const float* sp = s + (long long)n * C + cv * VEC;
+                Vec16<T> o;
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    const float gg = (float)to_acc<T>(gv.v[k]);
+                    o.v[k] = from_acc<T>(gg * (float)to_acc<T>(from_acc<T>(sp[k])));
+                    acc[j][k] += gg * (float)to_acc<T>(xv.v[k]);
+                }
+                st16_stream(gx + e, o);
+            }
+        }
+    }
+    write_partial<VEC>(g, acc, red, partial + ((long long)n * bands + band) * C, C);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float u, float alpha, float gain, float clampv) {
+    float v = u;
+    if (ACT == A_LRELU) v = u > 0.f ? u : u * alpha;
+    v *= gain;
+    if (clampv >= 0.f) v = fminf(fmaxf(v, -clampv), clampv);
+    return v;
+}
+// derivative factor decided from the saved OUTPUT, as the reference plugin does (OPS/bias_act.cu:132-142)
+template <int ACT>
+__device__ __forceinline__ float act_slope(float y, float alpha, float gain, float clampv) {
+    float m = gain;
+    if (ACT == A_LRELU) m = (y > 0.f) ? gain : gain * alpha;
+    if (clampv >= 0.f && !(fabsf(y) < clampv)) m = 0.f;
+    return m;
+}
+
+template <class T, int ACT>
+__global__ void __launch_bounds__(256) demod_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ d, const T* __restrict__ nz,
+                                                            const T* __restrict__ b, T* __restrict__ y, int C, long long P, long long total_vecs,
+                                                            float alpha, float gain, float clampv) {
+    constexpr int VEC = Vec16<T>::N;
+    const int cvecs = C / VEC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cvecs);
+        const long long pix = i / cvecs;       // n * P + p
+        const long long n = pix / P;
+        const Vec16<T> v = ld16_stream(x + i * VEC);
+        const float noise = nz ? (float)to_acc<T>(nz[pix]) : 0.f;
+        Vec16<T> bv;
+        if (b) bv = ld16(b + cv * VEC);
+        const float* dp = d ? d + n * C + cv * VEC : nullptr;
+        Vec16<T> o;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            float u = (float)to_acc<T>(v.v[k]);
+            if (dp) u *= (float)to_acc<T>(from_acc<T>(dp[k]));
+            u += noise;
+            // the reference materialises fma(x, d, noise) in T before bias_act reads it back (networks_stylegan2.py:71-72);
+            // rounding at the same point keeps the sign of near-zero pre-activations -- and with it the lrelu slope -- identical
+            if (dp || nz) u = (float)to_acc<T>(from_acc<T>(u));
+            if (b) u += (float)to_acc<T>(bv.v[k]);
+            o.v[k] = from_acc<T>(act_fwd<ACT>(u, alpha, gain, clampv));
+        }
+        st16_stream(y + i * VEC, o);
+    }
+}
+
+template <class T, int ACT>
+__global__ void __launch_bounds__(256) demod_act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yref, const T* __restrict__ x,
+                                                            const float* __restrict__ d, T* __restrict__ gx, T* __restrict__ gnz,
+                                                            float* __restrict__ partial1, float* __restrict__ partial0, int C, long long P,
+                                                            float alpha, float gain, float clampv) {
+    constexpr int VEC = Vec16<T>::N;
+    __shared__ float red[256 * VEC];
+    const BandGeom g = band_geom<VEC>(C);
+    const int band = blockIdx.x, bands = gridDim.x, n = blockIdx.y;
+    float acc1[MAXJ][VEC], acc0[MAXJ][VEC];
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc1[j][k] = acc0[j][k] = 0.f;
+    const long long base = (long long)n * P * C;
+    // every thread of a row group iterates the same number of times so that the shuffles below stay converged
+    const long long iters = (P - band + (long long)bands * g.rgroups - 1) / ((long long)bands * g.rgroups);
+    for (long long it = 0; it < iters; it++) {
+        const long long p = band + (long long)bands * (g.rg + g.rgroups * it);
+        const bool live = p < P;
+        float pix_sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++) {
+            const int cv = g.lane + g.lanes * j;
+            if (live && j < g.nj && cv < g.cvecs) {
+                const long long e = base + p * C + (long long)cv * VEC;
+                const Vec16<T> gv = ld16_stream(gy + e), yv = ld16_stream(yref + e);
+                Vec16<T> xv;
+                if (d) xv = ld16_stream(x + e);
+                const float* dp = d ? d + (long long)n * C + cv * VEC : nullptr;
+                Vec16<T> o;
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    const float g1 = (float)to_acc<T>(gv.v[k]) * act_slope<ACT>((float)to_acc<T>(yv.v[k]), alpha, gain, clampv);
+                    const float g1r = (float)to_acc<T>(from_acc<T>(g1));       // the reference materialises g1 in T before the fma backward
+                    pix_sum += g1r;
+                    acc0[j][k] += g1r;
+                    if (dp) {
+                        acc1[j][k] += g1r * (float)to_acc<T>(xv.v[k]);
+                        o.v[k] = from_acc<T>(g1r * (float)to_acc<T>(from_acc<T>(dp[k])));
+                    } else {
+                        o.v[k] = from_acc<T>(g1);
+                    }
+                }
+                st16_stream(gx + e, o);
+            }
+        }
+        if (gnz) {
+            // sum over the channels of this pixel: lanes of the row group are contiguous lanes of one warp (lanes <= 32)
+            for (int off = g.lanes >> 1; off > 0; off >>= 1) pix_sum += __shfl_xor_sync(0xffffffffu, pix_sum, off);
+            if (live && g.lane == 0) gnz[(long long)n * P + p] = from_acc<T>(pix_sum);
+        }
+    }
+    if (partial1) write_partial<VEC>(g, acc1, red, partial1 + ((long long)n * bands + band) * C, C);
+    write_partial<VEC>(g, acc0, red, partial0 + ((long long)n * bands + band) * C, C);
+}
+
+// out[n][c] = sum over bands (in order) of partial[n][band][c]
+__global__ void band_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int NC_n, int C, int bands) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)NC_n * C) return;
+    const long long n = i / C;
+    const int c = (int)(i - n * C);
+    float sum = 0.f;
+    for (int b = 0; b < bands; b++) sum += partial[(n * bands + b) * C + c];
+    out[i] = sum;
+}
+
+int pick_bands(int N, long long P, int C, int vec) {
+    const int cvecs = C / vec;
+    const int lanes = cvecs < 32 ? cvecs : 32;
+    const int rgroups = 256 / lanes;
+    long long bands = ((long long)gt_num_sms() * 8 + N - 1) / N;        // about 8 CTAs per SM in total
+    const long long maxb = (P + rgroups - 1) / rgroups;
+    if (bands > maxb) bands = maxb;
+    if (bands < 1) bands = 1;
+    return (int)bands;
+}
+
+int ew_grid(long long total_vecs) {
+    long long blocks = (total_vecs + 255) / 256;
+    const long long cap = (long long)gt_num_sms() * 16;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+template <class T>
+bool shape_ok(int N, long long P, int C) {
+    constexpr int VEC = Vec16<T>::N;
+    return N > 0 && P > 0 && C > 0 && C % VEC == 0 && C / VEC <= 32 * MAXJ && (C / VEC >= 32 ? (C / VEC) % 32 == 0 : (256 % (C / VEC)) == 0);
+}
+
+}  // namespace
+
+#define GT_MOD_DISPATCH(CALL_F32, CALL_F16)                                   \
+    if (dtype == GT_F32) { CALL_F32; }                                        \
+    else if (dtype == GT_F16) { CALL_F16; }                                   \
+    else { gt_set_error("modulated ops: unsupported dtype code %d", dtype); return GT_ERR_ARG; }
+
+extern "C" long long gt_mod_workspace(int N, long long P, int C, int dtype) {
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    if (N <= 0 || P <= 0 || C <= 0 || C % vec) return 0;
+    return 2ll * N * pick_bands(N, P, C, vec) * C;
+}
+
+extern "C" int gt_mod_scale_fwd(const void* x, const float* s, void* y, int dtype, int N, long long P, int C, void* stream) {
+    GT_REQUIRE(x && s && y, "gt_mod_scale_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    GT_REQUIRE(N > 0 && P > 0 && C > 0 && C % vec == 0, "gt_mod_scale_fwd: bad shape N=%d P=%lld C=%d", N, P, C);
+    const long long tv = (long long)N * P * (C / vec);
+    GT_MOD_DISPATCH((mod_scale_fwd_kernel<float><<<ew_grid(tv), 256, 0, st>>>((const float*)x, s, (float*)y, C, P, tv)),
+                    (mod_scale_fwd_kernel<__half><<<ew_grid(tv), 256, 0, st>>>((const __half*)x, s, (__half*)y, C, P, tv)));
+    GT_CUDA_LAUNCH_CHECK("gt_mod_scale_fwd");
+    return GT_OK;
+}
+
+extern "C" int gt_mod_scale_bwd(const void* gy, const void* x, const float* s, void* gx, float* gs, float* workspace, long long workspace_floats,
+                                int dtype, int N, long long P, int C, void* stream) {
+    GT_REQUIRE(gy && x && s && gx && gs && workspace, "gt_mod_scale_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    GT_REQUIRE((dtype == GT_F16 && shape_ok<__half>(N, P, C)) || (dtype == GT_F32 && shape_ok<float>(N, P, C)), "gt_mod_scale_bwd: unsupported shape N=%d P=%lld C=%d",
+               N, P, C);
+    const int bands = pick_bands(N, P, C, vec);
+    GT_REQUIRE((long long)N * bands * C <= workspace_floats, "gt_mod_scale_bwd: workspace too small");
+    dim3 grid(bands, N);
+    GT_MOD_DISPATCH((mod_scale_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)gy, (const float*)x, s, (float*)gx, workspace, C, P)),
+                    (mod_scale_bwd_kernel<__half><<<grid, 256, 0, st>>>((const __half*)gy, (const __half*)x, s, (__half*)gx, workspace, C, P)));
+    GT_CUDA_LAUNCH_CHECK("gt_mod_scale_bwd");
+    band_reduce_kernel<<<(int)(((long long)N * C + 255) / 256), 256, 0, st>>>(workspace, gs, N, C, bands);
+    GT_CUDA_LAUNCH_CHECK("gt_mod_scale_bwd(reduce)");
+    return GT_OK;
+}
+
+extern "C" int gt_demod_act_fwd(const void* x, const float* d, const void* noise, const void* b, void* y, int dtype, int act, float alpha, float gain,
+                                float clamp, int N, long long P, int C, void* stream) {
+    GT_REQUIRE(x && y, "gt_demod_act_fwd: null pointer");
+    GT_REQUIRE(act == A_LINEAR || act == A_LRELU, "gt_demod_act_fwd: only linear (1) and lrelu (3) are supported; got %d", act);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    GT_REQUIRE(N > 0 && P > 0 && C > 0 && C % vec == 0, "gt_demod_act_fwd: bad shape N=%d P=%lld C=%d", N, P, C);
+    const long long tv = (long long)N * P * (C / vec);
+    const int grid = ew_grid(tv);
+    if (act == A_LRELU) {
+        GT_MOD_DISPATCH((demod_act_fwd_kernel<float, A_LRELU><<<grid, 256, 0, st>>>((const float*)x, d, (const float*)noise, (const float*)b, (float*)y, C, P, tv, alpha, gain, clamp)),
+                        (demod_act_fwd_kernel<__half, A_LRELU><<<grid, 256, 0, st>>>((const __half*)x, d, (const __half*)noise, (const __half*)b, (__half*)y, C, P, tv, alpha, gain, clamp)));
+    } else {
+        GT_MOD_DISPATCH((demod_act_fwd_kernel<float, A_LINEAR><<<grid, 256, 0, st>>>((const float*)x, d, (const float*)noise, (const float*)b, (float*)y, C, P, tv, alpha, gain, clamp)),
+                        (demod_act_fwd_kernel<__half, A_LINEAR><<<grid, 256, 0, st>>>((const __half*)x, d, (const __half*)noise, (const __half*)b, (__half*)y, C, P, tv, alpha, gain, clamp)));
+    }
+    GT_CUDA_LAUNCH_CHECK("gt_demod_act_fwd");
+    return GT_OK;
+}
+
+extern "C" int gt_demod_act_bwd(const void* gy, const void* yref, const void* x, const float* d, void* gx, void* gnoise, float* gd, float* s0,
+                                float* workspace, long long workspace_floats, int dtype, int act, float alpha, float gain, float clamp, int N,
+                                long long P, int C, void* stream) {
+    GT_REQUIRE(gy && yref && gx && s0 && workspace, "gt_demod_act_bwd: null pointer");
+    GT_REQUIRE((d == nullptr) == (gd == nullptr) && (d == nullptr || x != nullptr), "gt_demod_act_bwd: d, gd and x go together");
+    GT_REQUIRE(act == A_LINEAR || act == A_LRELU, "gt_demod_act_bwd: only linear (1) and lrelu (3) are supported; got %d", act);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    GT_REQUIRE((dtype == GT_F16 && shape_ok<__half>(N, P, C)) || (dtype == GT_F32 && shape_ok<float>(N, P, C)), "gt_demod_act_bwd: unsupported shape N=%d P=%lld C=%d",
+               N, P, C);
+    const int bands = pick_bands(N, P, C, vec);
+    const long long per = (long long)N * bands * C;
+    GT_REQUIRE(2 * per <= workspace_floats, "gt_demod_act_bwd: workspace too small");
+    float* p1 = d ? workspace : nullptr;
+    float* p0 = workspace + per;
+    dim3 grid(bands, N);
+    if (act == A_LRELU) {
+        GT_MOD_DISPATCH((demod_act_bwd_kernel<float, A_LRELU><<<grid, 256, 0, st>>>((const float*)gy, (const float*)yref, (const float*)x, d, (float*)gx, (float*)gnoise, p1, p0, C, P, alpha, gain, clamp)),
+                        (demod_act_bwd_kernel<__half, A_LRELU><<<grid, 256, 0, st>>>((const __half*)gy, (const __half*)yref, (const __half*)x, d, (__half*)gx, (__half*)gnoise, p1, p0, C, P, alpha, gain, clamp)));
+    } else {
+        GT_MOD_DISPATCH((demod_act_bwd_kernel<float, A_LINEAR><<<grid, 256, 0, st>>>((const float*)gy, (const float*)yref, (const float*)x, d, (float*)gx, (float*)gnoise, p1, p0, C, P, alpha, gain, clamp)),
+                        (demod_act_bwd_kernel<__half, A_LINEAR><<<grid, 256, 0, st>>>((const __half*)gy, (const __half*)yref, (const __half*)x, d, (__half*)gx, (__half*)gnoise, p1, p0, C, P, alpha, gain, clamp)));
+    }
+    GT_CUDA_LAUNCH_CHECK("gt_demod_act_bwd");
+    const int rgrid = (int)(((long long)N * C + 255) / 256);
+    if (d) {
+        band_reduce_kernel<<<rgrid, 256, 0, st>>>(p1, gd, N, C, bands);
+        GT_CUDA_LAUNCH_CHECK("gt_demod_act_bwd(reduce gd)");
+    }
+    band_reduce_kernel<<<rgrid, 256, 0, st>>>(p0, s0, N, C, bands);
+    GT_CUDA_LAUNCH_CHECK("gt_demod_act_bwd(reduce s0)");
+    return GT_OK;
+}

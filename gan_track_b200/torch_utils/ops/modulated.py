@@ -1,0 +1,205 @@
+"""Fused element-wise halves of the training-mode modulated convolution (csrc/modulated.cu) on channels-last tensors.
+
+    mod_scale(x, s)                         = x * s.to(x.dtype)[:, :, None, None]               networks_stylegan2.py:69
+    demod_act(x, d, noise, b, act, ...)     = bias_act(fma(x, d.to(x.dtype)[:, :, None, None], noise), b, act, gain, clamp)
+                                                                                              networks_stylegan2.py:71-72, 325-327
+Each is ONE pass over the activation instead of one per torch op; each backward is ONE pass that also produces every
+reduction (style / demodulation-coefficient / noise / bias gradients) in a fixed order.  Both first-order backward
+functions are themselves differentiable (the path-length regulariser differentiates the generator's backward,
+S3/training/loss.py:85-100); the second-order formulas are written with plain torch ops since they only run in the lazy
+Greg phase.
+
+`applicable(x)` says whether a tensor can take the fused route (CUDA, fp16/fp32, dense channels-last, channel count the
+kernels support); callers keep the reference's op-by-op sequence otherwise.
+"""
+import torch
+
+from ... import _lib
+
+_ACT = {'linear': 1, 'lrelu': 3}
+
+
+def applicable(x):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.ndim == 4 and x.dtype in (torch.float16, torch.float32)):
+        return False
+    n, c, h, w = x.shape
+    vec = 8 if x.dtype == torch.float16 else 4
+    if c % vec or n == 0 or h * w == 0:
+        return False
+    cv = c // vec
+    if not ((cv < 32 and 256 % cv == 0) or (cv >= 32 and cv % 32 == 0 and cv <= 128)):
+        return False
+    s = x.stride()
+    return s[1] == 1 and s[3] == c and s[2] == w * c and s[0] == h * w * c and x.data_ptr() % 16 == 0
+
+
+def _cl(t):
+    return t if applicable(t) else t.contiguous(memory_format=torch.channels_last)
+
+
+def _ws(x):
+    n, c, h, w = x.shape
+    lib = _lib.load()
+    nws = lib.gt_mod_workspace(n, h * w, c, _lib.dtype_code(x))
+    return torch.empty([nws], dtype=torch.float32, device=x.device), nws
+
+
+def _bc(v, like):
+    """[N,C] fp32 -> [N,C,1,1] in like.dtype"""
+    return v.to(like.dtype).reshape(v.shape[0], v.shape[1], 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------------- mod_scale
+
+class _ModScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        n, c, h, w = x.shape
+        s = s.to(torch.float32).contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gt_mod_scale_fwd(_lib.ptr(x), _lib.ptr(s), _lib.ptr(y), _lib.dtype_code(x), n, h * w, c, _lib.stream_of(x)), 'gt_mod_scale_fwd')
+        _lib.count_launch()
+        ctx.save_for_backward(x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s = ctx.saved_tensors
+        gx, gs = _ModScaleGrad.apply(gy, x, s)
+        return (gx if ctx.needs_input_grad[0] else None), (gs if ctx.needs_input_grad[1] else None)
+
+
+class _ModScaleGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gy, x, s):
+        gy = _cl(gy)
+        n, c, h, w = x.shape
+        gx = torch.empty_like(x)
+        gs = torch.empty([n, c], dtype=torch.float32, device=x.device)
+        ws, nws = _ws(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gt_mod_scale_bwd(_lib.ptr(gy), _lib.ptr(x), _lib.ptr(s), _lib.ptr(gx), _lib.ptr(gs), _lib.ptr(ws), nws,
+                                                    _lib.dtype_code(x), n, h * w, c, _lib.stream_of(x)), 'gt_mod_scale_bwd')
+        _lib.count_launch(2)
+        ctx.save_for_backward(gy, x, s)
+        return gx, gs
+
+    @staticmethod
+    def backward(ctx, ggx, ggs):
+        # gx = gy * s,  gs = sum_hw gy * x   =>   second-order terms below
+        gy, x, s = ctx.saved_tensors
+        d_gy = d_x = d_s = None
+        if ctx.needs_input_grad[0]:
+            d_gy = 0
+            if ggx is not None:
+                d_gy = d_gy + ggx * _bc(s, x)
+            if ggs is not None:
+                d_gy = d_gy + _bc(ggs, x) * x
+        if ctx.needs_input_grad[1] and ggs is not None:
+            d_x = _bc(ggs, x) * gy
+        if ctx.needs_input_grad[2] and ggx is not None:
+            d_s = (ggx.to(torch.float32) * gy.to(torch.float32)).sum(dim=[2, 3])
+        return d_gy, d_x, d_s
+
+
+def mod_scale(x, s):
+    """x: [N,C,H,W] channels-last; s: [N,C] (any float dtype; applied in x.dtype as the reference does)."""
+    return _ModScale.apply(x, s)
+
+
+# ------------------------------------------------------------------------------------------------------- demod_act
+
+def _slope(y, act, alpha, gain, clamp):
+    """gain * act'(.) * [|y| < clamp], decided from the saved output like the reference plugin (OPS/bias_act.cu:132-142)."""
+    m = torch.full_like(y, gain)
+    if act == 'lrelu':
+        m = torch.where(y > 0, m, m * alpha)
+    if clamp >= 0:
+        m = m * (y.abs() < clamp).to(y.dtype)
+    return m
+
+
+class _DemodAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, d, noise, b, act, alpha, gain, clamp):
+        n, c, h, w = x.shape
+        d32 = d.to(torch.float32).contiguous() if d is not None else None
+        nz = noise.to(x.dtype).expand(n, 1, h, w).contiguous() if noise is not None else None
+        bb = b.to(x.dtype).contiguous() if b is not None else None
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gt_demod_act_fwd(_lib.ptr(x), _lib.ptr(d32), _lib.ptr(nz), _lib.ptr(bb), _lib.ptr(y), _lib.dtype_code(x), _ACT[act],
+                                                    alpha, gain, clamp, n, h * w, c, _lib.stream_of(x)), 'gt_demod_act_fwd')
+        _lib.count_launch()
+        ctx.save_for_backward(x if d is not None else None, d32, y)
+        ctx.cfg = (act, alpha, gain, clamp, noise is not None, tuple(noise.shape) if noise is not None else None, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, d, y = ctx.saved_tensors
+        act, alpha, gain, clamp, has_nz, nz_shape, has_b = ctx.cfg
+        gx, gd, gnz, s0 = _DemodActGrad.apply(gy, y, x, d, act, alpha, gain, clamp, has_nz and ctx.needs_input_grad[2])
+        g_noise = None
+        if has_nz and ctx.needs_input_grad[2]:
+            g_noise = gnz
+            if tuple(gnz.shape) != nz_shape:                     # noise was broadcast (e.g. [H,W] constant noise)
+                g_noise = gnz.sum_to_size(nz_shape)
+        g_b = s0.sum(dim=0).to(y.dtype) if (has_b and ctx.needs_input_grad[3]) else None
+        return (gx if ctx.needs_input_grad[0] else None), (gd if (d is not None and ctx.needs_input_grad[1]) else None), g_noise, g_b, None, None, None, None
+
+
+class _DemodActGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gy, y, x, d, act, alpha, gain, clamp, want_noise):
+        gy = _cl(gy)
+        n, c, h, w = y.shape
+        gx = torch.empty_like(y)
+        gd = torch.empty([n, c], dtype=torch.float32, device=y.device) if d is not None else None
+        s0 = torch.empty([n, c], dtype=torch.float32, device=y.device)
+        gnz = torch.empty([n, 1, h, w], dtype=y.dtype, device=y.device) if want_noise else None
+        ws, nws = _ws(y)
+        with torch.cuda.device(y.device):
+            _lib.check(_lib.load().gt_demod_act_bwd(_lib.ptr(gy), _lib.ptr(y), _lib.ptr(x), _lib.ptr(d), _lib.ptr(gx), _lib.ptr(gnz), _lib.ptr(gd), _lib.ptr(s0),
+                                                    _lib.ptr(ws), nws, _lib.dtype_code(y), _ACT[act], alpha, gain, clamp, n, h * w, c, _lib.stream_of(y)),
+                       'gt_demod_act_bwd')
+        _lib.count_launch(3 if d is not None else 2)
+        ctx.save_for_backward(gy, y, x, d)
+        ctx.cfg = (act, alpha, gain, clamp)
+        return gx, gd, gnz, s0
+
+    @staticmethod
+    def backward(ctx, ggx, ggd, ggnz, ggs0):
+        # With m = gain * act'(y) * [|y| < clamp] (piecewise constant) and g1 = gy * m:
+        #   gx = g1 * d,  gd = sum_hw g1 * x,  gnz = sum_c g1,  s0 = sum_hw g1
+        gy, y, x, d = ctx.saved_tensors
+        act, alpha, gain, clamp = ctx.cfg
+        m = _slope(y, act, alpha, gain, clamp)
+        d_gy = d_x = d_d = None
+        if ctx.needs_input_grad[0]:
+            t = 0
+            if ggx is not None:
+                t = t + (ggx * _bc(d, y) if d is not None else ggx)
+            if ggd is not None and d is not None:
+                t = t + _bc(ggd, y) * x
+            if ggnz is not None:
+                t = t + ggnz.to(y.dtype)
+            if ggs0 is not None:
+                t = t + _bc(ggs0, y)
+            d_gy = m * t if not isinstance(t, int) else None
+        g1 = None
+        if d is not None and ctx.needs_input_grad[2] and ggd is not None:
+            g1 = gy * m
+            d_x = _bc(ggd, y) * g1
+        if d is not None and ctx.needs_input_grad[3] and ggx is not None:
+            g1 = gy * m if g1 is None else g1
+            d_d = (ggx.to(torch.float32) * g1.to(torch.float32)).sum(dim=[2, 3])
+        return d_gy, None, d_x, d_d, None, None, None, None, None
+
+
+def demod_act(x, d=None, noise=None, b=None, act='linear', alpha=0.2, gain=1.0, clamp=None):
+    """clamp(act(x * d[n,c] + noise + b[c]) * gain) on a channels-last tensor.  d: [N,C] or None; noise: broadcastable to
+    [N,1,H,W] or None; b: [C] or None; act in {'linear', 'lrelu'}; clamp None or < 0 disables clamping."""
+    assert act in _ACT
+    return _DemodAct.apply(x, d, noise, b, act, float(alpha), float(gain), float(clamp) if clamp is not None else -1.0)

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..torch_utils import misc
-from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
+from ..torch_utils.ops import bias_act, conv2d_resample, fma, modulated, upfirdn2d
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -32,6 +32,8 @@ def modulated_conv2d(
     demodulate=True,
     flip_weight=True,           # True = correlation (torch conv2d)
     fused_modconv=True,         # True: per-sample weights + grouped conv; False: scale activations around a shared-weight conv
+    bias_act_args=None,         # (not in the reference) dict(b, act, gain, clamp): apply the layer's bias_act here, so that on
+                                # channels-last CUDA tensors demodulation + noise + bias + activation run as one fused pass
 ):
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
@@ -52,16 +54,29 @@ def modulated_conv2d(
         wsq = weight.square().sum(dim=[2, 3])                                   # [O, I]
         dcoefs = (styles.square() @ wsq.t() + 1e-8).rsqrt()                     # [N, O]
 
+    def finish(x):
+        if bias_act_args is None:
+            return x
+        return bias_act.bias_act(x, bias_act_args['b'], act=bias_act_args['act'], gain=bias_act_args['gain'], clamp=bias_act_args['clamp'])
+
     if not fused_modconv:
-        x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
+        if modulated.applicable(x):
+            x = modulated.mod_scale(x, styles)                                   # one pass forward, one pass backward (gx and gs)
+        else:
+            x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
         x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
+        if bias_act_args is not None and bias_act_args['act'] in ('linear', 'lrelu') and modulated.applicable(x):
+            spec = bias_act.activation_funcs[bias_act_args['act']]
+            gain = bias_act_args['gain'] if bias_act_args['gain'] is not None else spec.def_gain
+            return modulated.demod_act(x, dcoefs if demodulate else None, noise, bias_act_args['b'], act=bias_act_args['act'], alpha=spec.def_alpha,
+                                       gain=gain, clamp=bias_act_args['clamp'])
         if demodulate and noise is not None:
             x = fma.fma(x, dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1), noise.to(x.dtype))
         elif demodulate:
             x = x * dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1)
         elif noise is not None:
             x = x.add_(noise.to(x.dtype))
-        return x
+        return finish(x)
 
     # Fused: fold style (and demodulation) into per-sample weights, run as one grouped convolution.
     w = weight.unsqueeze(0) * styles.reshape(batch_size, 1, -1, 1, 1)          # [N, O, I, kh, kw]
@@ -73,7 +88,7 @@ def modulated_conv2d(
     x = x.reshape(batch_size, -1, *x.shape[2:])
     if noise is not None:
         x = x.add_(noise)
-    return x
+    return finish(x)
 
 
 class FullyConnectedLayer(torch.nn.Module):
@@ -227,10 +242,10 @@ class SynthesisLayer(torch.nn.Module):
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
+        return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
+                                bias_act_args=dict(b=self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp))
 
     def extra_repr(self):
         return (f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, w_dim={self.w_dim:d}, '

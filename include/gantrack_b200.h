@@ -117,6 +117,26 @@ int gt_aug_warp_fwd(const float* x, const float* theta, const int* margins, cons
 int gt_aug_warp_bwd(const float* gy, const float* theta, const int* margins, const float* taps_host, int ntaps, float* gx, int B,
                     int C, int H, int W, int OH, int OW, void* stream);
 
+/* ---- fused element-wise halves of the training-mode modulated convolution (channels-last [N, P = H*W, C]) ------------
+ * Replace the torch op sequences of S3/training/networks_stylegan2.py:69 (x * styles), :71-72 (fma with the demodulation
+ * coefficients and noise, OPS/fma.py:15-58) and :325-327 (bias_act) and their backward passes.  s, d, gs, gd, s0: fp32
+ * [N,C]; noise / gnoise: [N,P] in the tensor dtype; b: [C] in the tensor dtype; act: 1 linear or 3 lrelu.
+ *   gt_mod_scale_fwd:  y = x * s[n,c]
+ *   gt_mod_scale_bwd:  gx = gy * s[n,c];  gs[n,c] = sum_p gy * x
+ *   gt_demod_act_fwd:  y = clamp(act(x * d[n,c] + noise[n,p] + b[c]) * gain)          (d, noise, b may each be NULL)
+ *   gt_demod_act_bwd:  g1 = gy * gain * act'(yref) * [|yref| < clamp];  gx = g1 * d[n,c];  gd[n,c] = sum_p g1 * x;
+ *                      s0[n,c] = sum_p g1;  gnoise[n,p] = sum_c g1                       (d/gd/x NULL together; gnoise may be NULL)
+ * workspace: fp32, at least gt_mod_workspace(N, P, C, dtype) floats.  Reductions have a fixed order. */
+long long gt_mod_workspace(int N, long long P, int C, int dtype);
+int gt_mod_scale_fwd(const void* x, const float* s, void* y, int dtype, int N, long long P, int C, void* stream);
+int gt_mod_scale_bwd(const void* gy, const void* x, const float* s, void* gx, float* gs, float* workspace,
+                     long long workspace_floats, int dtype, int N, long long P, int C, void* stream);
+int gt_demod_act_fwd(const void* x, const float* d, const void* noise, const void* b, void* y, int dtype, int act, float alpha,
+                     float gain, float clamp, int N, long long P, int C, void* stream);
+int gt_demod_act_bwd(const void* gy, const void* yref, const void* x, const float* d, void* gx, void* gnoise, float* gd,
+                     float* s0, float* workspace, long long workspace_floats, int dtype, int act, float alpha, float gain,
+                     float clamp, int N, long long P, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
