@@ -15,6 +15,10 @@
 // up/down in {1,2}; 12-tap separable passes of the ADA pipe) and fall back to run-time loops otherwise.
 #include "gt_common.cuh"
 
+int gt_upfirdn2d_try_tma(const void* x, const float* f, long long fs_h, long long fs_w, int flip, float gain, void* y, int dtype, int N, int C, int H, int W,
+                         long long xs_n, long long xs_h, long long xs_w, int OH, int OW, long long ys_n, long long ys_h, long long ys_w, int padx0, int pady0,
+                         cudaStream_t st);
+
 namespace {
 
 struct UpfirdnParams {
@@ -264,6 +268,12 @@ extern "C" int gt_upfirdn2d(const void* x, const float* f, void* y, int dtype, i
     p.ys_n = ys_n; p.ys_c = ys_c; p.ys_h = ys_h; p.ys_w = ys_w;
     p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain;
     cudaStream_t st = (cudaStream_t)stream;
+    if (upx == 1 && upy == 1 && downx == 1 && downy == 1 && fh == 4 && fw == 4 && xs_c == 1 && ys_c == 1 && (dtype == GT_F16 || dtype == GT_F32) &&
+        (long long)N * OH * OW * C >= (1 << 20)) {
+        // the blur around the resampling convolutions on channels-last tensors: TMA-staged kernel (upfirdn2d_tma.cu)
+        const int rc = gt_upfirdn2d_try_tma(x, f, fs_h, fs_w, flip ? 1 : 0, gain, y, dtype, N, C, H, W, xs_n, xs_h, xs_w, OH, OW, ys_n, ys_h, ys_w, padx0, pady0, st);
+        if (rc >= 0) return rc;
+    }
     switch (dtype) {
         case GT_F32: return dispatch<float>(p, st);
         case GT_F16: return dispatch<__half>(p, st);
