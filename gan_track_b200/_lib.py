@@ -20,6 +20,7 @@ _PROTOTYPES = {
     'gt_last_error': (_c.c_char_p, []),
     'gt_abi_version': (_i, []),
     'gt_sm_count': (_i, []),
+    'gt_stream_config': (_i, [_i]),
     'gt_bias_act': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _ll, _i, _ll, _vp]),
     'gt_bias_act_bwd_workspace': (_ll, [_i, _i, _ll]),
     'gt_bias_act_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _i, _i, _ll, _vp]),

@@ -9,6 +9,8 @@
 // path.  gt_bias_act_bwd additionally produces the per-channel bias gradient in the same pass (the reference
 // re-reads dx with a separate torch reduction, OPS/bias_act.py:169-170).
 #include "gt_common.cuh"
+#include "stream_bulk.cuh"
+#include "hot_act.cuh"
 #include <math.h>
 
 namespace {
@@ -91,6 +93,32 @@ __global__ void __launch_bounds__(256) bias_act_scalar_kernel(BiasActParams p) {
     }
 }
 
+
+// One 16-byte vector of the hot path (linear / lrelu, grad 0 or 1) with the lean packed arithmetic of hot_act.cuh.
+// v0: x (grad 0) or dy (grad 1), replaced by the result; yv: saved forward output (grad 1); bv: the vector's bias lanes
+// as fp32 pairs (grad 0 only, may be zeros).
+template <class T, int ACT>
+__device__ __forceinline__ void hot_vector(Vec16<T>& v0, const Vec16<T>& yv, const float2* bv, int grad, bool clamp_on, const hot::Params& hp) {
+    typedef hot::Lanes<T> L;
+    if (grad == 0) {
+        if (clamp_on) {
+#pragma unroll
+            for (int i = 0; i < L::NP; i++) L::set(v0, i, hot::fwd<ACT, true>(__fadd2_rn(L::get(v0, i), bv[i]), hp));
+        } else {
+#pragma unroll
+            for (int i = 0; i < L::NP; i++) L::set(v0, i, hot::fwd<ACT, false>(__fadd2_rn(L::get(v0, i), bv[i]), hp));
+        }
+    } else {
+        if (clamp_on) {
+#pragma unroll
+            for (int i = 0; i < L::NP; i++) L::set(v0, i, hot::bwd<ACT, true>(L::get(v0, i), L::get(yv, i), hp));
+        } else {
+#pragma unroll
+            for (int i = 0; i < L::NP; i++) L::set(v0, i, hot::bwd<ACT, false>(L::get(v0, i), L::get(yv, i), hp));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Vector path for linear / lrelu (the only activations on the StyleGAN2 path).  BMODE: 0 = no bias, 1 = bias constant
 // across a 16-byte vector (step_b % VEC == 0, e.g. NCHW), 2 = bias varies per element with step_b == 1 and
@@ -106,6 +134,8 @@ __global__ void __launch_bounds__(256) bias_act_vec_kernel(BiasActParams p) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const S alpha = (S)p.alpha, gain = (S)p.gain, clampv = (S)p.clamp;
     const int grad = p.grad;
+    const hot::Params hp = hot::make_params(p.alpha, p.gain, p.clamp);
+    const bool clamp_on = p.clamp >= 0.f && (p.grad == 0 || USE_YREF);   // without a saved output the clamp cannot mask the gradient
     long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; iv < nvec; iv += stride * UNROLL) {
         Vec16<T> xv[UNROLL], yv[UNROLL];
@@ -122,20 +152,21 @@ __global__ void __launch_bounds__(256) bias_act_vec_kernel(BiasActParams p) {
             long long j = iv + u * stride;
             if (j < nvec) {
                 long long e0 = j * VEC;
-                S bs = (S)0;
-                Vec16<T> bv;
-                if (BMODE == 1 && grad == 0) bs = to_acc<T>(__ldg(b + (e0 / p.step_b) % p.size_b));
-                if (BMODE == 2 && grad == 0) bv = ld16(b + (e0 % p.size_b));
-                Vec16<T> o;
+                float2 bf[hot::Lanes<T>::NP];
 #pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    S v = to_acc<T>(xv[u].v[k]);
-                    if (BMODE == 1) v += bs;
-                    if (BMODE == 2 && grad == 0) v += to_acc<T>(bv.v[k]);
-                    S yrv = USE_YREF ? to_acc<T>(yv[u].v[k]) : (S)0;
-                    o.v[k] = from_acc<T>(act_eval<ACT, S>(v, (S)0, yrv, (S)1, grad, alpha, gain, clampv));
+                for (int i = 0; i < hot::Lanes<T>::NP; i++) bf[i] = make_float2(0.f, 0.f);
+                if (BMODE == 1 && grad == 0) {
+                    const float bs = (float)to_acc<T>(__ldg(b + (e0 / p.step_b) % p.size_b));
+#pragma unroll
+                    for (int i = 0; i < hot::Lanes<T>::NP; i++) bf[i] = make_float2(bs, bs);
                 }
-                st16_stream(y + e0, o);
+                if (BMODE == 2 && grad == 0) {
+                    const Vec16<T> bv = ld16(b + (e0 % p.size_b));
+#pragma unroll
+                    for (int i = 0; i < hot::Lanes<T>::NP; i++) bf[i] = hot::Lanes<T>::get(bv, i);
+                }
+                hot_vector<T, ACT>(xv[u], yv[u], bf, grad, clamp_on, hp);
+                st16_stream(y + e0, xv[u]);
             }
         }
     }
@@ -149,6 +180,87 @@ __global__ void __launch_bounds__(256) bias_act_vec_kernel(BiasActParams p) {
             y[i] = from_acc<T>(act_eval<ACT, S>(v, (S)0, yrv, (S)1, grad, alpha, gain, clampv));
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk-staged vector path (stream_bulk.cuh): same arithmetic as bias_act_vec_kernel, data moved by the bulk copy engine.
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, int ACT, int BMODE, bool USE_YREF>
+__global__ void __launch_bounds__(streamk::NTHREADS) bias_act_bulk_kernel(BiasActParams p) {
+    typedef typename Acc<T>::type S;
+    constexpr int VEC = Vec16<T>::N;
+    extern __shared__ uint8_t smem_raw[];
+    const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* yr = (const T*)p.yref; T* y = (T*)p.y;
+    const S alpha = (S)p.alpha, gain = (S)p.gain, clampv = (S)p.clamp;
+    const int grad = p.grad;
+    const hot::Params hp = hot::make_params(p.alpha, p.gain, p.clamp);
+    const bool clamp_on = p.clamp >= 0.f && (p.grad == 0 || USE_YREF);   // without a saved output the clamp cannot mask the gradient
+    typedef hot::Lanes<T> L;
+    // channels-last bias: a thread's vectors always cover the same channels when size_b divides 256 * VEC -> fetch once
+    const bool fixed_b = BMODE == 2 && grad == 0 && (256 * VEC) % p.size_b == 0;
+    float2 bfix[L::NP];
+#pragma unroll
+    for (int i = 0; i < L::NP; i++) bfix[i] = make_float2(0.f, 0.f);
+    if (fixed_b) {
+        const Vec16<T> bv = ld16(b + ((int)threadIdx.x * VEC) % p.size_b);
+#pragma unroll
+        for (int i = 0; i < L::NP; i++) bfix[i] = L::get(bv, i);
+    }
+    auto body = [&](long long e0, Vec16<T>& v0, const Vec16<T>& v1, const Vec16<T>&) {
+        if (BMODE == 0 || grad != 0 || fixed_b) {
+            hot_vector<T, ACT>(v0, v1, bfix, grad, clamp_on, hp);
+        } else {
+            float2 bf[L::NP];
+            if (BMODE == 1) {
+                const float bs = (float)to_acc<T>(__ldg(b + (e0 / p.step_b) % p.size_b));
+#pragma unroll
+                for (int i = 0; i < L::NP; i++) bf[i] = make_float2(bs, bs);
+            } else {
+                const Vec16<T> bv = ld16(b + (e0 % p.size_b));
+#pragma unroll
+                for (int i = 0; i < L::NP; i++) bf[i] = L::get(bv, i);
+            }
+            hot_vector<T, ACT>(v0, v1, bf, grad, clamp_on, hp);
+        }
+    };
+    if (USE_YREF) streamk::run<T, 2, 6, 8192>(x, yr, (const T*)nullptr, y, p.size_x, smem_raw, body);
+    else streamk::run<T, 1, 6, 16384>(x, (const T*)nullptr, (const T*)nullptr, y, p.size_x, smem_raw, body);
+    // ragged tail (size_x % VEC elements)
+    if (blockIdx.x == 0) {
+        long long i = (p.size_x / VEC) * VEC + threadIdx.x;
+        if (i < p.size_x) {
+            S v = to_acc<T>(x[i]);
+            if (BMODE != 0 && grad == 0) v += to_acc<T>(b[(i / p.step_b) % p.size_b]);
+            S yrv = USE_YREF ? to_acc<T>(yr[i]) : (S)0;
+            y[i] = from_acc<T>(act_eval<ACT, S>(v, (S)0, yrv, (S)1, grad, alpha, gain, clampv));
+        }
+    }
+}
+
+template <class K>
+int bulk_smem_attr(K kernel, int bytes, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        gt_set_error("%s: cannot reserve %d bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));
+        return GT_ERR_CUDA;
+    }
+    return GT_OK;
+}
+
+template <class T, int ACT, int BMODE, bool USE_YREF>
+int launch_bulk_t(const BiasActParams& p, cudaStream_t st) {
+    constexpr int SMEM = USE_YREF ? streamk::Smem<2, 6, 8192>::TOTAL : streamk::Smem<1, 6, 16384>::TOTAL;
+    static bool configured = false;
+    if (!configured) {
+        int rc = bulk_smem_attr(bias_act_bulk_kernel<T, ACT, BMODE, USE_YREF>, SMEM, "gt_bias_act(bulk)");
+        if (rc != GT_OK) return rc;
+        configured = true;
+    }
+    const int grid = streamk::grid_for(p.size_x, (int)sizeof(T), USE_YREF ? 8192 : 16384, 2);
+    bias_act_bulk_kernel<T, ACT, BMODE, USE_YREF><<<grid, streamk::NTHREADS, SMEM, st>>>(p);
+    GT_CUDA_LAUNCH_CHECK("gt_bias_act(bulk)");
+    return GT_OK;
 }
 
 template <class T, int ACT>
@@ -182,6 +294,10 @@ template <class T, int ACT, int BMODE>
 int launch_vec(const BiasActParams& p, cudaStream_t st) {
     constexpr int VEC = Vec16<T>::N;
     long long nvec = p.size_x / VEC;
+    if (gt_stream_variant() == 0 && p.size_x * (long long)sizeof(T) >= (1ll << 22)) {   // >= 4 MB: bulk-staged streaming
+        if (p.yref) return launch_bulk_t<T, ACT, BMODE, true>(p, st);
+        return launch_bulk_t<T, ACT, BMODE, false>(p, st);
+    }
     // 4 vectors per thread per trip; whole waves of 8 resident 256-thread CTAs per SM.
     long long blocks = (nvec + 256 * 4 - 1) / (256 * 4);
     long long wave = (long long)gt_num_sms() * 8;
@@ -237,6 +353,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_plane_kernel(const T* __rest
     constexpr int VEC = Vec16<T>::N;
     const int c = blockIdx.x % C;
     const int slice = blockIdx.x / C;
+    const hot::Params hp = hot::make_params(alpha, gain, clampv);
     float acc = 0.f;
     const bool vec_ok = (inner % VEC == 0);
     for (int n = slice; n < outer; n += slices) {
@@ -245,11 +362,14 @@ __global__ void __launch_bounds__(256) bias_act_bwd_plane_kernel(const T* __rest
             for (long long i = (long long)threadIdx.x * VEC; i < inner; i += 256 * VEC) {
                 Vec16<T> g = ld16_stream(dy + base + i), yv, o;
                 if (yref) yv = ld16_stream(yref + base + i);
+                if (!yref) yv = g;
+                o = g;
+                hot_vector<T, ACT>(o, yv, nullptr, 1, yref != nullptr && clampv >= 0.f, hp);
 #pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    float r = act_eval<ACT, float>((float)to_acc<T>(g.v[k]), 0.f, yref ? (float)to_acc<T>(yv.v[k]) : 0.f, 1.f, 1, alpha, gain, clampv);
-                    o.v[k] = from_acc<T>(r);
-                    acc += (float)to_acc<T>(o.v[k]);   // sum what is stored, like dx.sum() on the stored tensor
+                for (int k = 0; k < hot::Lanes<T>::NP; k++) {
+                    const float2 st = hot::Lanes<T>::stored(o, k);   // sum what is stored, like dx.sum() on the stored tensor
+                    acc += st.x;
+                    acc += st.y;
                 }
                 st16_stream(dx + base + i, o);
             }
@@ -284,6 +404,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_cl_kernel(const T* __restric
                                                               float alpha, float gain, float clampv) {
     constexpr int VEC = Vec16<T>::N;
     __shared__ float red[256 * VEC];
+    const hot::Params hp = hot::make_params(alpha, gain, clampv);
     const int band = blockIdx.x;
     const int cvecs = C / VEC;
     const int lanes = cvecs < 256 ? cvecs : 256;
@@ -300,11 +421,14 @@ __global__ void __launch_bounds__(256) bias_act_bwd_cl_kernel(const T* __restric
                 long long e0 = r * C + (long long)cv * VEC;
                 Vec16<T> g = ld16_stream(dy + e0), yv, o;
                 if (yref) yv = ld16_stream(yref + e0);
+                if (!yref) yv = g;
+                o = g;
+                hot_vector<T, ACT>(o, yv, nullptr, 1, yref != nullptr && clampv >= 0.f, hp);
 #pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    float v = act_eval<ACT, float>((float)to_acc<T>(g.v[k]), 0.f, yref ? (float)to_acc<T>(yv.v[k]) : 0.f, 1.f, 1, alpha, gain, clampv);
-                    o.v[k] = from_acc<T>(v);
-                    acc[k] += (float)to_acc<T>(o.v[k]);
+                for (int k = 0; k < hot::Lanes<T>::NP; k++) {
+                    const float2 st = hot::Lanes<T>::stored(o, k);
+                    acc[2 * k] += st.x;
+                    acc[2 * k + 1] += st.y;
                 }
                 st16_stream(dx + e0, o);
             }
@@ -321,6 +445,49 @@ __global__ void __launch_bounds__(256) bias_act_bwd_cl_kernel(const T* __restric
             }
         }
         __syncthreads();
+    }
+}
+
+
+// Bulk-staged variant of bias_act_bwd_cl_kernel.  A thread's vectors always cover the same VEC channels (see
+// stream_bulk.cuh), so the bias-gradient partial sums live in registers; they are combined across the CTA through shared
+// memory in a fixed order.  Partials: partial[blockIdx.x * C + c].
+template <class T, int ACT, bool USE_YREF>
+__global__ void __launch_bounds__(streamk::NTHREADS) bias_act_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ yref, T* __restrict__ dx,
+                                                                float* __restrict__ partial, int C, long long nelem, float alpha, float gain,
+                                                                float clampv) {
+    constexpr int VEC = Vec16<T>::N;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ float red[256 * VEC];
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k++) acc[k] = 0.f;
+    const hot::Params hp = hot::make_params(alpha, gain, clampv);
+    const bool clamp_on = USE_YREF && clampv >= 0.f;
+    auto body = [&](long long, Vec16<T>& v0, const Vec16<T>& v1, const Vec16<T>&) {
+        hot_vector<T, ACT>(v0, USE_YREF ? v1 : v0, nullptr, 1, clamp_on, hp);
+#pragma unroll
+        for (int k = 0; k < hot::Lanes<T>::NP; k++) {
+            const float2 st = hot::Lanes<T>::stored(v0, k);   // sum what is stored, like dx.sum() on the stored tensor
+            acc[2 * k] += st.x;
+            acc[2 * k + 1] += st.y;
+        }
+    };
+    if (USE_YREF) streamk::run<T, 2, 6, 8192>(dy, yref, (const T*)nullptr, dx, nelem, smem_raw, body);
+    else streamk::run<T, 1, 6, 16384>(dy, (const T*)nullptr, (const T*)nullptr, dx, nelem, smem_raw, body);
+    if (threadIdx.x < 256) {              // (the copy-engine driver warp holds no sums)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) red[threadIdx.x * VEC + k] = acc[k];
+    }
+    __syncthreads();
+    const int cvecs = C / VEC;
+    if ((int)threadIdx.x < cvecs) {
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            float s = 0.f;
+            for (int g2 = threadIdx.x; g2 < 256; g2 += cvecs) s += red[g2 * VEC + k];
+            partial[(long long)blockIdx.x * C + threadIdx.x * VEC + k] = s;
+        }
     }
 }
 
@@ -375,6 +542,35 @@ static int bias_act_bwd_t(const T* dy, const T* yref, T* dx, float* db, float* w
             bias_act_bwd_plane_kernel<T, A_LRELU><<<C * slices, 256, 0, st>>>(dy, yref, dx, ws, C, inner, outer, slices, alpha, gain, clamp);
     } else {
         long long rows = outer;
+        const long long nelem = rows * C;
+        const bool al = ((((uintptr_t)dy) | ((uintptr_t)dx) | ((uintptr_t)yref)) & 15) == 0;
+        if (gt_stream_variant() == 0 && al && (256 * VEC) % C == 0 && nelem * (long long)sizeof(T) >= (1ll << 22)) {
+            const int ch = yref ? 8192 : 16384;
+            const int grid = streamk::grid_for(nelem, (int)sizeof(T), ch, 2);
+            parts = grid;
+            GT_REQUIRE((long long)parts * C <= ws_floats, "gt_bias_act_bwd: workspace too small (%lld floats, need %lld)", ws_floats, (long long)parts * C);
+#define GT_BWD_BULK(ACT_, YR_)                                                                                                         \
+    {                                                                                                                                   \
+        constexpr int SMEM = YR_ ? streamk::Smem<2, 6, 8192>::TOTAL : streamk::Smem<1, 6, 16384>::TOTAL;                                  \
+        static bool configured = false;                                                                                                 \
+        if (!configured) {                                                                                                              \
+            int rc = bulk_smem_attr(bias_act_bwd_bulk_kernel<T, ACT_, YR_>, SMEM, "gt_bias_act_bwd(bulk)");                              \
+            if (rc != GT_OK) return rc;                                                                                                 \
+            configured = true;                                                                                                          \
+        }                                                                                                                               \
+        bias_act_bwd_bulk_kernel<T, ACT_, YR_><<<grid, streamk::NTHREADS, SMEM, st>>>(dy, yref, dx, ws, C, nelem, alpha, gain, clamp);                 \
+    }
+            if (act == A_LINEAR) {
+                if (yref) GT_BWD_BULK(A_LINEAR, true) else GT_BWD_BULK(A_LINEAR, false)
+            } else {
+                if (yref) GT_BWD_BULK(A_LRELU, true) else GT_BWD_BULK(A_LRELU, false)
+            }
+#undef GT_BWD_BULK
+            GT_CUDA_LAUNCH_CHECK("gt_bias_act_bwd(bulk)");
+            reduce_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, db, C, parts);
+            GT_CUDA_LAUNCH_CHECK("gt_bias_act_bwd(reduce)");
+            return GT_OK;
+        }
         int bands = sms * 4;
         if (bands > rows) bands = (int)rows;
         if (bands < 1) bands = 1;

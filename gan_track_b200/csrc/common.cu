@@ -26,3 +26,12 @@ int gt_num_sms() {
 extern "C" const char* gt_last_error(void) { return g_err; }
 extern "C" int gt_abi_version(void) { return 1; }
 extern "C" int gt_sm_count(void) { return gt_num_sms(); }
+
+// Tuning switch for the HBM-streaming kernels: 0 = bulk-copy staged (default), 1 = direct vector loads/stores.
+static int g_stream_variant = 0;
+int gt_stream_variant() { return g_stream_variant; }
+extern "C" int gt_stream_config(int variant) {
+    const int old = g_stream_variant;
+    g_stream_variant = variant;
+    return old;
+}

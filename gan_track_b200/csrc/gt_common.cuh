@@ -36,6 +36,30 @@ void gt_set_error(const char* fmt, ...);
 
 // ---- device properties (cached per process; the library keeps no other global state) ---------------------------
 int gt_num_sms();
+int gt_stream_variant();   // 0 = bulk-copy staged streaming kernels, 1 = direct vector loads/stores (tuning / A-B)
+
+
+// ---- division by a run-time constant without the ~40-instruction integer divide --------------------------------
+// floor(n / d) for 0 <= n < 2^31 and 1 <= d < 2^31 (Granlund-Montgomery: m = ceil(2^(31+l) / d), l = ceil(log2 d)).
+struct FastDiv {
+    uint32_t m, sh, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) l++;
+    f.m = (uint32_t)(((1ull << (31 + l)) + d - 1) / d);
+    f.sh = 31 + l;
+    f.d = d;
+    return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return (uint32_t)(((unsigned long long)n * f.m) >> f.sh); }
+// n -> (n / d, n % d)
+__device__ __forceinline__ uint32_t fd_divmod(uint32_t n, const FastDiv& f, uint32_t& rem) {
+    const uint32_t q = fd_div(n, f);
+    rem = n - q * f.d;
+    return q;
+}
 
 // ---- scalar type traits: I/O type -> accumulation type (fp16 I/O computes in fp32, like OPS/bias_act.cu:15-18) --
 template <class T> struct Acc { typedef float type; };
@@ -48,7 +72,7 @@ template <class T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v
 template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half_rn(v); }
 
 // ---- 16-byte vector I/O ---------------------------------------------------------------------------------------
-template <class T> struct Vec16 { static constexpr int N = 16 / sizeof(T); T v[16 / sizeof(T)]; };
+template <class T> struct alignas(16) Vec16 { static constexpr int N = 16 / sizeof(T); T v[16 / sizeof(T)]; };
 
 template <class T> __device__ __forceinline__ Vec16<T> ld16(const T* p) {
     Vec16<T> r;

@@ -91,11 +91,156 @@ __global__ void __launch_bounds__(128) upfirdn2d_row_kernel(UpfirdnParams p) {
     }
 }
 
+
+// ---- small W-contiguous planes (the fp32 4x4..32x32 blocks of G and D, NCHW) ---------------------------------------
+// A CTA stages PL whole input planes in shared memory with coalesced loads (a plane is one contiguous run of H*W
+// elements), then its threads produce the PL output planes, again as contiguous runs.  Every tap is a shared-memory
+// read; global memory sees each input element once.  Same index algebra as the row kernel.
+template <class T, int UPX, int UPY, int DOWNX, int DOWNY, int FW, int FH>
+__global__ void __launch_bounds__(256) upfirdn2d_plane_kernel(UpfirdnParams p, int PL) {
+    typedef typename Acc<T>::type S;
+    extern __shared__ float smem_f[];
+    const int upx = UPX ? UPX : p.upx, upy = UPY ? UPY : p.upy;
+    const int downx = DOWNX ? DOWNX : p.downx, downy = DOWNY ? DOWNY : p.downy;
+    const int fw = FW ? FW : p.fw, fh = FH ? FH : p.fh;
+    float* sf = smem_f;                       // taps
+    S* sx = (S*)(smem_f + ((fh * fw + 3) & ~3));   // PL staged planes
+    stage_taps(p, sf);
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    const int in_sz = p.H * p.W, out_sz = p.OH * p.OW;
+    const long long planes = (long long)p.N * p.C;
+    for (long long g0 = (long long)blockIdx.x * PL; g0 < planes; g0 += (long long)gridDim.x * PL) {
+        const int npl = (int)((planes - g0) < PL ? (planes - g0) : PL);
+        for (int i = threadIdx.x; i < npl * in_sz; i += 256) {
+            const int pl = i / in_sz, e = i - pl * in_sz;
+            const long long plane = g0 + pl;
+            const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
+            sx[i] = to_acc<T>(x[n * p.xs_n + c * p.xs_c + e]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < npl * out_sz; i += 256) {
+            const int pl = i / out_sz, e = i - pl * out_sz;
+            const int oy = e / p.OW, ox = e - oy * p.OW;
+            const S* xp = sx + pl * in_sz;
+            const int by = oy * downy - p.pady0, bx = ox * downx - p.padx0;
+            const int ky0 = pos_mod(-by, upy), kx0 = pos_mod(-bx, upx);
+            S acc = (S)0;
+            if constexpr (FH != 0) {
+                constexpr int NKY = (FH + UPY - 1) / UPY, NKX = (FW + UPX - 1) / UPX;
+#pragma unroll
+                for (int j = 0; j < NKY; j++) {
+                    const int ky = ky0 + j * UPY;
+                    const int iy = (by + ky) / UPY;
+                    if (ky < FH && iy >= 0 && iy < p.H) {
+#pragma unroll
+                        for (int i2 = 0; i2 < NKX; i2++) {
+                            const int kx = kx0 + i2 * UPX;
+                            const int ix = (bx + kx) / UPX;
+                            if (kx < FW && ix >= 0 && ix < p.W) acc += xp[iy * p.W + ix] * (S)sf[ky * FW + kx];
+                        }
+                    }
+                }
+            } else {
+                for (int ky = ky0; ky < fh; ky += upy) {
+                    const int iy = (by + ky) / upy;
+                    if (iy < 0 || iy >= p.H) continue;
+                    for (int kx = kx0; kx < fw; kx += upx) {
+                        const int ix = (bx + kx) / upx;
+                        if (ix >= 0 && ix < p.W) acc += xp[iy * p.W + ix] * (S)sf[ky * fw + kx];
+                    }
+                }
+            }
+            const long long plane = g0 + pl;
+            const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
+            y[n * p.ys_n + c * p.ys_c + e] = from_acc<T>(acc);
+        }
+        __syncthreads();
+    }
+}
+
+
+// 4x4 taps, up = down = 1, non-negative padding on small W-contiguous planes (the blur around the resampling convolutions of
+// the fp32 4x4..16x16 blocks): the planes are staged ZERO-PADDED, so the inner loop has no bounds checks, and a thread
+// produces a strip of 4 adjacent outputs from 4 x (16+8+4)-byte shared-memory reads -- ~20 instructions per output instead
+// of ~160 for the gather form, which was issue-bound at 0.6 TB/s (ncu, profiles/).
+struct Plane44Div {
+    FastDiv in_sz, W, strips_per_plane, OW4, C;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) upfirdn2d_plane44_kernel(UpfirdnParams p, int PL, int PW, int PH, Plane44Div dv) {
+    extern __shared__ float smem_f[];
+    float* sf = smem_f;                 // 16 taps
+    float* sx = smem_f + 16;            // PL padded planes of PH x PW floats (PW a multiple of 4, 16-byte aligned rows)
+    stage_taps(p, sf);
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) g[i] = sf[i];
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    const int in_sz = p.H * p.W;
+    const int OW4 = (p.OW + 3) >> 2;
+    const int pplane = PH * PW;
+    for (int i = threadIdx.x; i < PL * pplane; i += 256) sx[i] = 0.f;     // borders stay zero for the whole kernel
+    __syncthreads();
+    const int planes = p.N * p.C;
+    const bool vec_out = (p.OW & 3) == 0 && sizeof(T) == 4;
+    for (int g0 = blockIdx.x * PL; g0 < planes; g0 += gridDim.x * PL) {
+        const int npl = (planes - g0) < PL ? (planes - g0) : PL;
+        for (int i = threadIdx.x; i < npl * in_sz; i += 256) {
+            uint32_t e, ix;
+            const uint32_t pl = fd_divmod((uint32_t)i, dv.in_sz, e);
+            const uint32_t iy = fd_divmod(e, dv.W, ix);
+            uint32_t c;
+            const uint32_t n = fd_divmod((uint32_t)g0 + pl, dv.C, c);
+            sx[pl * pplane + (iy + p.pady0) * PW + ix + p.padx0] = (float)to_acc<T>(x[n * p.xs_n + c * p.xs_c + e]);
+        }
+        __syncthreads();
+        const int strips = npl * p.OH * OW4;
+        for (int i = threadIdx.x; i < strips; i += 256) {
+            uint32_t r, xs;
+            const uint32_t pl = fd_divmod((uint32_t)i, dv.strips_per_plane, r);
+            const uint32_t oy = fd_divmod(r, dv.OW4, xs);
+            const int x0 = (int)xs << 2;
+            const float* row = sx + pl * pplane + oy * PW + x0;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 4; ky++) {
+                const float4 u = *reinterpret_cast<const float4*>(row + ky * PW);
+                const float2 v = *reinterpret_cast<const float2*>(row + ky * PW + 4);
+                const float w = row[ky * PW + 6];
+                const float g0_ = g[ky * 4 + 0], g1_ = g[ky * 4 + 1], g2_ = g[ky * 4 + 2], g3_ = g[ky * 4 + 3];
+                a0 += u.x * g0_ + u.y * g1_ + u.z * g2_ + u.w * g3_;
+                a1 += u.y * g0_ + u.z * g1_ + u.w * g2_ + v.x * g3_;
+                a2 += u.z * g0_ + u.w * g1_ + v.x * g2_ + v.y * g3_;
+                a3 += u.w * g0_ + v.x * g1_ + v.y * g2_ + w * g3_;
+            }
+            uint32_t c;
+            const uint32_t n = fd_divmod((uint32_t)g0 + pl, dv.C, c);
+            T* yp = y + n * p.ys_n + c * p.ys_c + oy * p.OW + x0;
+            if (vec_out) {
+                *reinterpret_cast<float4*>(yp) = make_float4(a0, a1, a2, a3);
+            } else {
+                yp[0] = from_acc<T>(a0);
+                if (x0 + 1 < p.OW) yp[1] = from_acc<T>(a1);
+                if (x0 + 2 < p.OW) yp[2] = from_acc<T>(a2);
+                if (x0 + 3 < p.OW) yp[3] = from_acc<T>(a3);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- channels-last layout ------------------------------------------------------------------------------------------
 // One thread = one output pixel x VEC channels.  Thread order: channel vectors fastest, then ox, oy, n  -> a warp
 // reads/writes contiguous 512 bytes whenever C*sizeof(T) >= 512.
+struct VecDiv {
+    FastDiv cvecs, OW, OH;
+};
+
 template <class T, int UPX, int UPY, int DOWNX, int DOWNY, int FW, int FH>
-__global__ void __launch_bounds__(256) upfirdn2d_vec_kernel(UpfirdnParams p) {
+__global__ void __launch_bounds__(256) upfirdn2d_vec_kernel(UpfirdnParams p, VecDiv dv) {
     constexpr int VEC = Vec16<T>::N;
     typedef typename Acc<T>::type S;
     extern __shared__ float sf[];
@@ -107,12 +252,15 @@ __global__ void __launch_bounds__(256) upfirdn2d_vec_kernel(UpfirdnParams p) {
     T* y = (T*)p.y;
     const int cvecs = p.C / VEC;
     const long long total = (long long)p.N * p.OH * p.OW * cvecs;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % cvecs);
-        long long r = i / cvecs;
-        const int ox = (int)(r % p.OW); r /= p.OW;
-        const int oy = (int)(r % p.OH);
-        const int n = (int)(r / p.OH);
+    // index split with multiply-shift division: (pixel-vector index within one image) -> cv, ox, oy; images walked by the outer loop
+    const uint32_t per_img = (uint32_t)(p.OH * p.OW * cvecs);
+    (void)per_img;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {   // total < 2^31 (launcher)
+        uint32_t cvu, oxu, oyu;
+        uint32_t r = fd_divmod(i, dv.cvecs, cvu);
+        r = fd_divmod(r, dv.OW, oxu);
+        const int n = (int)fd_divmod(r, dv.OH, oyu);
+        const int cv = (int)cvu, ox = (int)oxu, oy = (int)oyu;
         const T* xp = x + n * p.xs_n + (long long)cv * VEC;        // xs_c == 1
         const int by = oy * downy - p.pady0, bx = ox * downx - p.padx0;
         const int ky0 = pos_mod(-by, upy), kx0 = pos_mod(-bx, upx);
@@ -200,6 +348,49 @@ int launch_row(const UpfirdnParams& p, cudaStream_t st) {
     return GT_OK;
 }
 
+
+constexpr int PLANE_MAX_ELEMS = 8192;   // staged input elements per CTA (32 KB of fp32)
+
+template <class T, int UPX, int UPY, int DOWNX, int DOWNY, int FW, int FH>
+int launch_plane(const UpfirdnParams& p, cudaStream_t st) {
+    typedef typename Acc<T>::type S;
+    const int in_sz = p.H * p.W;
+    const long long planes = (long long)p.N * p.C;
+    int PL = PLANE_MAX_ELEMS / in_sz;
+    if (PL > 16) PL = 16;
+    // keep at least ~2 CTAs per SM busy
+    while (PL > 1 && (planes + PL - 1) / PL < (long long)gt_num_sms() * 2) PL >>= 1;
+    long long groups = (planes + PL - 1) / PL;
+    long long cap = (long long)gt_num_sms() * 8;
+    unsigned grid = (unsigned)(groups < cap ? groups : cap);
+    size_t smem = (size_t)((p.fh * p.fw + 3) & ~3) * sizeof(float) + (size_t)PL * in_sz * sizeof(S);
+    upfirdn2d_plane_kernel<T, UPX, UPY, DOWNX, DOWNY, FW, FH><<<grid, 256, smem, st>>>(p, PL);
+    GT_CUDA_LAUNCH_CHECK("gt_upfirdn2d(plane)");
+    return GT_OK;
+}
+
+template <class T>
+int launch_plane44(const UpfirdnParams& p, cudaStream_t st) {
+    const int PW = ((p.OW + 3) & ~3) + 4, PH = p.OH + 3;
+    const long long planes = (long long)p.N * p.C;
+    int PL = PLANE_MAX_ELEMS / (PW * PH);
+    if (PL > 16) PL = 16;
+    while (PL > 1 && (planes + PL - 1) / PL < (long long)gt_num_sms() * 2) PL >>= 1;
+    long long groups = (planes + PL - 1) / PL;
+    long long cap = (long long)gt_num_sms() * 6;
+    unsigned grid = (unsigned)(groups < cap ? groups : cap);
+    size_t smem = (size_t)(16 + PL * PW * PH) * sizeof(float);
+    Plane44Div dv;
+    dv.in_sz = make_fastdiv((uint32_t)(p.H * p.W));
+    dv.W = make_fastdiv((uint32_t)p.W);
+    dv.strips_per_plane = make_fastdiv((uint32_t)(p.OH * ((p.OW + 3) >> 2)));
+    dv.OW4 = make_fastdiv((uint32_t)((p.OW + 3) >> 2));
+    dv.C = make_fastdiv((uint32_t)p.C);
+    upfirdn2d_plane44_kernel<T><<<grid, 256, smem, st>>>(p, PL, PW, PH, dv);
+    GT_CUDA_LAUNCH_CHECK("gt_upfirdn2d(plane44)");
+    return GT_OK;
+}
+
 template <class T, int UPX, int UPY, int DOWNX, int DOWNY, int FW, int FH>
 int launch_vec(const UpfirdnParams& p, cudaStream_t st) {
     constexpr int VEC = Vec16<T>::N;
@@ -207,7 +398,11 @@ int launch_vec(const UpfirdnParams& p, cudaStream_t st) {
     long long blocks = (total + 255) / 256;
     long long cap = (long long)gt_num_sms() * 8 * 4;
     unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
-    upfirdn2d_vec_kernel<T, UPX, UPY, DOWNX, DOWNY, FW, FH><<<grid, 256, p.fh * p.fw * sizeof(float), st>>>(p);
+    VecDiv dv;
+    dv.cvecs = make_fastdiv((uint32_t)(p.C / VEC));
+    dv.OW = make_fastdiv((uint32_t)p.OW);
+    dv.OH = make_fastdiv((uint32_t)p.OH);
+    upfirdn2d_vec_kernel<T, UPX, UPY, DOWNX, DOWNY, FW, FH><<<grid, 256, p.fh * p.fw * sizeof(float), st>>>(p, dv);
     GT_CUDA_LAUNCH_CHECK("gt_upfirdn2d(vec)");
     return GT_OK;
 }
@@ -221,13 +416,24 @@ int dispatch(const UpfirdnParams& p, cudaStream_t st) {
     constexpr int VEC = Vec16<T>::N;
     const bool small_f = p.fh * p.fw <= MAX_TAPS_SMEM;
     const bool al = ((((uintptr_t)p.x) | ((uintptr_t)p.y)) & 15) == 0;
-    const bool cl = small_f && al && p.xs_c == 1 && p.ys_c == 1 && p.C % VEC == 0 && p.C >= VEC && p.xs_w % VEC == 0 && p.xs_h % VEC == 0 &&
+    const bool cl = small_f && al && p.xs_c == 1 && p.ys_c == 1 && p.C % VEC == 0 && p.C >= VEC && (long long)p.N * p.OH * p.OW * (p.C / VEC) < (1ll << 31) && p.xs_w % VEC == 0 && p.xs_h % VEC == 0 &&
                     p.xs_n % VEC == 0 && p.ys_w % VEC == 0 && p.ys_h % VEC == 0 && p.ys_n % VEC == 0;
     if (cl) {
         GT_UPFIRDN_CASE(launch_vec, 1, 1, 1, 1, 4, 4)
         GT_UPFIRDN_CASE(launch_vec, 2, 2, 1, 1, 4, 4)
         GT_UPFIRDN_CASE(launch_vec, 1, 1, 2, 2, 4, 4)
         return launch_vec<T, 0, 0, 0, 0, 0, 0>(p, st);
+    }
+    if (small_f && p.xs_w == 1 && p.ys_w == 1 && p.xs_h == p.W && p.ys_h == p.OW && p.H * p.W <= PLANE_MAX_ELEMS && p.OH * p.OW <= 4 * PLANE_MAX_ELEMS &&
+        (long long)p.N * p.C >= 64 && (long long)p.N * p.C < (1ll << 30) && sizeof(T) <= 4) {
+        if (p.upx == 1 && p.upy == 1 && p.downx == 1 && p.downy == 1 && p.fw == 4 && p.fh == 4 && p.padx0 >= 0 && p.pady0 >= 0 &&
+            p.OW + 3 - p.W - p.padx0 >= 0 && p.OH + 3 - p.H - p.pady0 >= 0 && p.ys_h == p.OW &&
+            (((p.OW + 3) & ~3) + 4) * (p.OH + 3) <= PLANE_MAX_ELEMS && (p.ys_n % 4 == 0) && (p.ys_c % 4 == 0) && (((uintptr_t)p.y) & 15) == 0)
+            return launch_plane44<T>(p, st);
+        GT_UPFIRDN_CASE(launch_plane, 1, 1, 1, 1, 4, 4)
+        GT_UPFIRDN_CASE(launch_plane, 2, 2, 1, 1, 4, 4)
+        GT_UPFIRDN_CASE(launch_plane, 1, 1, 2, 2, 4, 4)
+        if (p.fh * p.fw <= 64) return launch_plane<T, 0, 0, 0, 0, 0, 0>(p, st);
     }
     if (small_f && p.xs_w == 1 && p.ys_w == 1) {
         GT_UPFIRDN_CASE(launch_row, 1, 1, 1, 1, 4, 4)

@@ -7,22 +7,24 @@
 // run at HBM speed, which a thread-per-output gather (16 predicated global loads per output) does not.
 //
 // Structure: persistent CTAs walk tiles of TW x TH output pixels x one 128-byte channel chunk (64 fp16 / 32 fp32
-// channels).  One elected thread keeps a 3-deep ring of TMA box loads in flight ((TW+3) x (TH+3) pixels, out-of-bounds
+// channels).  One elected thread keeps a 2-deep ring of TMA box loads in flight per CTA (two CTAs per SM) ((TW+3) x (TH+3) pixels, out-of-bounds
 // rows/columns zero-filled by the TMA unit = the op's zero padding), so the loads of the next tiles overlap the
-// arithmetic of the current one.  256 threads = TW columns x 8 channel vectors x 4 row groups; a thread walks its rows
-// with a rotating set of FH accumulators, so every staged row is read from shared memory once (FW 16-byte loads) and
-// every output is written with one 16-byte store; a warp writes 512 contiguous bytes.
+// arithmetic of the current one.  256 threads = 8 column pairs x 8 channel vectors x 4 row groups; a thread walks its rows
+// with a rotating set of FH accumulators per column, so every staged row is read from shared memory once (5 16-byte
+// loads for 2 output columns) and every output is written with one 16-byte store.
 #include "gt_common.cuh"
 #include "gt_sm100.cuh"
+#include "hot_act.cuh"
 
 using namespace sm100;
 
 namespace {
 
-constexpr int TW = 8, TH = 16, FW = 4, FH = 4, STAGES = 3;
+constexpr int TW = 16, TH = 16, FW = 4, FH = 4, STAGES = 2;
 constexpr int BOX_W = TW + FW - 1, BOX_H = TH + FH - 1;
 constexpr int STAGE_BYTES = BOX_W * BOX_H * 128;
 constexpr int RG = 4, ROWS_PER_THREAD = TH / RG;   // 4 row groups of 4 output rows
+constexpr int CPT = 2;                             // output columns per thread
 
 struct FirParams {
     void* y;
@@ -35,14 +37,25 @@ struct FirParams {
     float gain;
 };
 
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+// The kernel is issue-bound before it is HBM-bound (ncu, profiles/: 205 warp instructions per 16-byte output vector in
+// the first version), so the arithmetic is organised to minimise instructions: every thread owns 2 adjacent output
+// columns x 4 output rows x one 16-byte channel vector; per staged row it reads 5 vectors once, converts them to fp32
+// once, and -- when the 4x4 filter is an outer product, which every StyleGAN2 resampling filter is
+// (upfirdn2d.setup_filter([1,3,3,1])) -- applies the horizontal taps first and feeds the result to the rotating
+// vertical accumulators, all with packed fp32x2 FMAs.  A filter that is not rank-1 takes the general 16-tap path.
 template <class T>
-__global__ void __launch_bounds__(256) upfirdn2d_tma_kernel(const __grid_constant__ CUtensorMap tmX, const FirParams p, const int total_tiles) {
-    constexpr int VEC = Vec16<T>::N;               // 8 fp16 / 4 fp32 per 16 bytes; a 128-byte chunk is 8 vectors either way
-    typedef typename Acc<T>::type S;
+__global__ void __launch_bounds__(256, 2) upfirdn2d_tma_kernel(const __grid_constant__ CUtensorMap tmX, const FirParams p, const int total_tiles) {
+    typedef hot::Lanes<T> L;
+    constexpr int NP = L::NP;                      // float2 pairs per 16-byte vector (4 fp16 / 2 fp32)
+    constexpr int VEC = Vec16<T>::N;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
     __shared__ float sf[FH * FW];
+    __shared__ float sgx[FW], sgy[FH];
+    __shared__ int s_sep;
     if (threadIdx.x < FH * FW) {   // correlation taps: g = f if flip else f reversed, gain folded in (OPS/upfirdn2d.py:196-199)
         const int ky = threadIdx.x / FW, kx = threadIdx.x - ky * FW;
         const int sy = p.flip ? ky : FH - 1 - ky, sx = p.flip ? kx : FW - 1 - kx;
@@ -50,13 +63,32 @@ __global__ void __launch_bounds__(256) upfirdn2d_tma_kernel(const __grid_constan
     }
 
     const int tid = threadIdx.x;
-    const int cv = tid & 7, col = (tid >> 3) & (TW - 1), rg = tid >> 6;
+    const int cv = tid & 7, cp = (tid >> 3) & 7, rg = tid >> 6;
     if (tid == 0) {
         tma_prefetch_desc(&tmX);
         for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    if (tid == 0) {
+        // rank-1 test: g[ky][kx] == gy[ky] * gx[kx] with gx = pivot row, gy = pivot column / pivot
+        int pr = 0, pc = 0;
+        float best = 0.f;
+        for (int i = 0; i < FH * FW; i++)
+            if (fabsf(sf[i]) > best) {
+                best = fabsf(sf[i]);
+                pr = i / FW;
+                pc = i % FW;
+            }
+        int sep = best > 0.f;
+        if (sep) {
+            for (int kx = 0; kx < FW; kx++) sgx[kx] = sf[pr * FW + kx];
+            for (int ky = 0; ky < FH; ky++) sgy[ky] = sf[ky * FW + pc] / sf[pr * FW + pc];
+            for (int i = 0; i < FH * FW; i++)
+                if (fabsf(sf[i] - sgy[i / FW] * sgx[i % FW]) > 1e-7f * best) sep = 0;
+        }
+        s_sep = sep;
+    }
 
     auto issue = [&](int tile, int stage) {
         int t = tile;
@@ -77,11 +109,13 @@ __global__ void __launch_bounds__(256) upfirdn2d_tma_kernel(const __grid_constan
             if (tile < total_tiles) issue(tile, s);
         }
     }
-    S g[FH][FW];
+    __syncthreads();
+    const bool sep = s_sep != 0;
+    float gx[FW], gy[FH];
 #pragma unroll
-    for (int ky = 0; ky < FH; ky++)
+    for (int k = 0; k < FW; k++) gx[k] = sgx[k];
 #pragma unroll
-        for (int kx = 0; kx < FW; kx++) g[ky][kx] = (S)sf[ky * FW + kx];
+    for (int k = 0; k < FH; k++) gy[k] = sgy[k];
 
     int it = 0;
     for (int tile = first; tile < total_tiles; tile += step, it++) {
@@ -94,41 +128,75 @@ __global__ void __launch_bounds__(256) upfirdn2d_tma_kernel(const __grid_constan
         t /= p.tiles_x;
         const int ty = t % p.tiles_y;
         const int n = t / p.tiles_y;
-        const int ox = tx * TW + col;
+        const int ox = tx * TW + cp * CPT;
         const int oy0 = ty * TH + rg * ROWS_PER_THREAD;
-        const uint8_t* sp = smem + stage * STAGE_BYTES + ((rg * ROWS_PER_THREAD) * BOX_W + col) * 128 + cv * 16;
+        const uint32_t sp = smem_u32(smem) + stage * STAGE_BYTES + ((rg * ROWS_PER_THREAD) * BOX_W + cp * CPT) * 128 + cv * 16;
         T* yp = (T*)p.y + (long long)n * p.ys_n + (long long)ox * p.ys_w + (long long)ch * (128 / (int)sizeof(T)) + cv * VEC;
 
-        S acc[FH][VEC];
+        float2 acc[FH][CPT][NP];
 #pragma unroll
         for (int a = 0; a < FH; a++)
 #pragma unroll
-            for (int k = 0; k < VEC; k++) acc[a][k] = (S)0;
-        // staged rows t = 0 .. ROWS_PER_THREAD + FH - 2 of this thread's strip; output row o = t - ky
+            for (int c = 0; c < CPT; c++)
+#pragma unroll
+                for (int k = 0; k < NP; k++) acc[a][c][k] = splat(0.f);
+        // staged rows tr = 0 .. ROWS_PER_THREAD + FH - 2 of this thread's strip; output row o = tr - ky
 #pragma unroll
         for (int tr = 0; tr < ROWS_PER_THREAD + FH - 1; tr++) {
+            float2 v[CPT + FW - 1][NP];
 #pragma unroll
-            for (int kx = 0; kx < FW; kx++) {
-                Vec16<T> v;
-                *reinterpret_cast<uint4*>(v.v) = *reinterpret_cast<const uint4*>(sp + (tr * BOX_W + kx) * 128);
+            for (int j = 0; j < CPT + FW - 1; j++) {
+                Vec16<T> raw;
+                *reinterpret_cast<uint4*>(raw.v) = lds128(sp + (tr * BOX_W + j) * 128);
+#pragma unroll
+                for (int k = 0; k < NP; k++) v[j][k] = L::get(raw, k);
+            }
+            if (sep) {
+#pragma unroll
+                for (int c = 0; c < CPT; c++) {
+                    float2 h[NP];
+#pragma unroll
+                    for (int k = 0; k < NP; k++) {
+                        h[k] = __fmul2_rn(v[c][k], splat(gx[0]));
+#pragma unroll
+                        for (int kx = 1; kx < FW; kx++) h[k] = __ffma2_rn(v[c + kx][k], splat(gx[kx]), h[k]);
+                    }
+#pragma unroll
+                    for (int ky = 0; ky < FH; ky++) {
+                        if (tr - ky >= 0 && tr - ky < ROWS_PER_THREAD) {
+#pragma unroll
+                            for (int k = 0; k < NP; k++) acc[(tr - ky) % FH][c][k] = __ffma2_rn(h[k], splat(gy[ky]), acc[(tr - ky) % FH][c][k]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
                 for (int ky = 0; ky < FH; ky++) {
                     if (tr - ky >= 0 && tr - ky < ROWS_PER_THREAD) {
 #pragma unroll
-                        for (int k = 0; k < VEC; k++) acc[(tr - ky) % FH][k] += to_acc<T>(v.v[k]) * g[ky][kx];
+                        for (int c = 0; c < CPT; c++)
+#pragma unroll
+                            for (int kx = 0; kx < FW; kx++) {
+                                const float w = sf[ky * FW + kx];
+#pragma unroll
+                                for (int k = 0; k < NP; k++) acc[(tr - ky) % FH][c][k] = __ffma2_rn(v[c + kx][k], splat(w), acc[(tr - ky) % FH][c][k]);
+                            }
                     }
                 }
             }
             const int o = tr - (FH - 1);
             if (o >= 0) {
                 const int oy = oy0 + o;
-                Vec16<T> out;
 #pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    out.v[k] = from_acc<T>(acc[o % FH][k]);
-                    acc[o % FH][k] = (S)0;
+                for (int c = 0; c < CPT; c++) {
+                    Vec16<T> out;
+#pragma unroll
+                    for (int k = 0; k < NP; k++) {
+                        L::set(out, k, acc[o % FH][c][k]);
+                        acc[o % FH][c][k] = splat(0.f);
+                    }
+                    if (ox + c < p.OW && oy < p.OH) st16_stream(yp + (long long)oy * p.ys_h + (long long)c * p.ys_w, out);
                 }
-                if (ox < p.OW && oy < p.OH) st16_stream(yp + (long long)oy * p.ys_h, out);
             }
         }
         __syncthreads();                       // every thread is done reading this stage
@@ -151,7 +219,7 @@ int launch_tma(const CUtensorMap& tm, const FirParams& p, int total_tiles, cudaS
         }
         configured = true;
     }
-    int grid = gt_num_sms() * 2;
+    int grid = gt_num_sms() * 2;        // two CTAs per SM (2 x 92 KB of staging): 16 warps hide the shared-memory / FMA latencies
     if (grid > total_tiles) grid = total_tiles;
     upfirdn2d_tma_kernel<T><<<grid, 256, SMEM, st>>>(tm, p, total_tiles);
     GT_CUDA_LAUNCH_CHECK("gt_upfirdn2d(tma)");

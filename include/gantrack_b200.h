@@ -35,6 +35,9 @@ const char* gt_last_error(void);
 int gt_abi_version(void);
 /* Number of SMs of the current device (148 on B200). */
 int gt_sm_count(void);
+/* Tuning / A-B switch of the HBM-streaming kernels (bias_act, modulation): 0 = bulk-copy staged through shared memory
+ * (default), 1 = direct 16-byte vector loads/stores.  Returns the previous value.  Results are identical. */
+int gt_stream_config(int variant);
 
 /* ---- bias_act ---------------------------------------------------------------------------------------------------
  * Replaces `bias_act_plugin.bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`

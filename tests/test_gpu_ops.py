@@ -163,6 +163,39 @@ def test_bias_act_full_size_properties(shape, cl):
     assert_close(db.float(), dx.float().sum([0, 2, 3]), 5e-3, 'db')
 
 
+@pytest.mark.parametrize('shape,cl,dtype', [((32, 64, 256, 256), True, torch.float16), ((32, 64, 128, 128), False, torch.float16),
+                                            ((16, 128, 65, 33), True, torch.float16), ((8, 512, 32, 32), True, torch.float32),
+                                            ((5, 64, 129, 131), True, torch.float16), ((1, 1, 1237, 1733), False, torch.float16)])
+def test_bias_act_bulk_staged_equals_direct(shape, cl, dtype):
+    """The bulk-copy staged streaming kernels (csrc/stream_bulk.cuh) and the direct vector kernels compute the same
+    thing bit for bit: forward, dx and db, incl. sizes that are not a whole number of chunks / vectors."""
+    from gan_track_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(1)
+    x = torch.randn(shape, device=DEV).to(dtype)
+    b = torch.randn(shape[1], device=DEV).to(dtype)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    dy = torch.randn_like(x)
+    out = []
+    for variant in (0, 1):
+        old = lib.gt_stream_config(variant)
+        try:
+            xr, br = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            y = bias_act.bias_act(xr, br, act='lrelu', gain=float(np.sqrt(2)), clamp=1.5)
+            dx, db = torch.autograd.grad(y, [xr, br], dy)
+            y2 = bias_act.bias_act(xr.detach(), None, act='linear', gain=0.5)
+            out.append((y.detach(), dx, db, y2))
+        finally:
+            lib.gt_stream_config(old)
+    torch.cuda.synchronize()
+    for a, c, name in zip(out[0], out[1], ['y', 'dx', 'db', 'y_linear']):
+        if name == 'db':
+            assert_close(a.float(), c.float(), 2e-3, name)       # different partial-sum grouping
+        else:
+            assert torch.equal(a, c), name
+
+
 # ---------------------------------------------------------------------------------------------------- upfirdn2d
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.float64])

@@ -52,16 +52,51 @@ for name, shape, dt, cl, kw in [
     ms = bench(lambda: upfirdn2d.upfirdn2d(x, f, **kw))
     rows.append((f'upfirdn2d {name}', nbytes, ms))
 
-xb = torch.randn([32, 64, 256, 256], device=dev).to(torch.float16).contiguous(memory_format=torch.channels_last)
-b = torch.randn([64], device=dev, dtype=torch.float16)
-ms = bench(lambda: bias_act.bias_act(xb, b, act='lrelu', clamp=256.0))
-rows.append(('bias_act fwd lrelu [32,64,256,256] f16 NHWC', 2 * xb.numel() * 2, ms))
-xg = xb.clone().requires_grad_(True)
-bg = b.clone().requires_grad_(True)
-yb = bias_act.bias_act(xg, bg, act='lrelu', clamp=256.0)
-dy = torch.randn_like(yb)
-ms = bench(lambda: torch.autograd.grad(yb, [xg, bg], dy, retain_graph=True))
-rows.append(('bias_act bwd (dx + db fused) [32,64,256,256] f16 NHWC', 3 * xb.numel() * 2, ms))
+from gan_track_b200 import _lib  # noqa: E402
+lib = _lib.load()
+for variant, vname in [(0, 'bulk-staged'), (1, 'direct')]:
+    lib.gt_stream_config(variant)
+    for shape in [(32, 64, 256, 256), (32, 256, 64, 64)]:
+        xb = torch.randn(shape, device=dev).to(torch.float16).contiguous(memory_format=torch.channels_last)
+        b = torch.randn([shape[1]], device=dev, dtype=torch.float16)
+        ms = bench(lambda: bias_act.bias_act(xb, b, act='lrelu', clamp=256.0))
+        rows.append((f'bias_act fwd lrelu {list(shape)} f16 NHWC ({vname})', 2 * xb.numel() * 2, ms))
+        xg = xb.clone().requires_grad_(True)
+        bg = b.clone().requires_grad_(True)
+        yb = bias_act.bias_act(xg, bg, act='lrelu', clamp=256.0)
+        dy = torch.randn_like(yb)
+        ms = bench(lambda: torch.autograd.grad(yb, [xg, bg], dy, retain_graph=True))
+        rows.append((f'bias_act bwd (dx + db fused) {list(shape)} f16 NHWC ({vname})', 3 * xb.numel() * 2, ms))
+        del xb, xg, yb, dy
+lib.gt_stream_config(0)
+# reference point: plain device-to-device copy of the same tensor size
+xc = torch.randn([32, 64, 256, 256], device=dev).to(torch.float16)
+yc = torch.empty_like(xc)
+ms = bench(lambda: yc.copy_(xc))
+rows.append(('torch copy_ [32,64,256,256] f16 (reference point)', 2 * xc.numel() * 2, ms))
+
+# modulation / demodulation+activation element-wise halves of the modulated convolution
+from gan_track_b200.torch_utils.ops import modulated  # noqa: E402
+for shape in [(32, 64, 256, 256), (32, 128, 128, 128)]:
+    n, c, h, w = shape
+    xm = torch.randn(shape, device=dev).to(torch.float16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    sm = torch.randn([n, c], device=dev).requires_grad_(True)
+    dm = torch.rand([n, c], device=dev).requires_grad_(True)
+    nz = torch.randn([n, 1, h, w], device=dev).to(torch.float16).requires_grad_(True)
+    bm = torch.randn([c], device=dev).to(torch.float16).requires_grad_(True)
+    nb = xm.numel() * 2
+    ms = bench(lambda: modulated.mod_scale(xm.detach(), sm.detach()))
+    rows.append((f'mod_scale fwd {list(shape)} f16 NHWC', 2 * nb, ms))
+    ym = modulated.mod_scale(xm, sm)
+    gy = torch.randn_like(ym)
+    ms = bench(lambda: torch.autograd.grad(ym, [xm, sm], gy, retain_graph=True))
+    rows.append((f'mod_scale bwd (gx + gs) {list(shape)} f16 NHWC', 3 * nb, ms))
+    ms = bench(lambda: modulated.demod_act(xm.detach(), dm.detach(), nz.detach(), bm.detach(), act='lrelu', gain=1.4142, clamp=256.0))
+    rows.append((f'demod_act fwd {list(shape)} f16 NHWC', 2 * nb, ms))
+    yd = modulated.demod_act(xm, dm, nz, bm, act='lrelu', gain=1.4142, clamp=256.0)
+    ms = bench(lambda: torch.autograd.grad(yd, [xm, dm, nz, bm], gy, retain_graph=True))
+    rows.append((f'demod_act bwd (gx + gd + gnoise + db) {list(shape)} f16 NHWC', 4 * nb, ms))
+    del xm, ym, yd, gy
 for name, nbytes, ms in rows:
     gbs = nbytes / ms / 1e6
-    print(f'{name:60s} {ms * 1e3:8.1f} us {gbs:8.0f} GB/s  {gbs / peak:5.2f} of measured HBM peak ({peak:.0f} GB/s)', flush=True)
+    print(f'{name:72s} {ms * 1e3:8.1f} us {gbs:8.0f} GB/s  {gbs / peak:5.2f} of measured HBM peak ({peak:.0f} GB/s)', flush=True)

@@ -7,7 +7,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from gan_track_b200.torch_utils.ops import bias_act, conv_igemm, upfirdn2d  # noqa: E402
+from gan_track_b200.torch_utils.ops import aug_warp, bias_act, conv_igemm, upfirdn2d  # noqa: E402
+from gan_track_b200.training import augment  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--reps', type=int, default=2)
@@ -28,7 +29,14 @@ x128 = t([32, 128, 128, 128]); wT = t([128, 64, 3, 3]) * 0.03             # G b2
 xb = t([32, 64, 257, 257])
 f = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
 b = torch.randn([64], device=dev, dtype=torch.float16)
+pipe = augment.AugmentPipe(xflip=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1)
+img = torch.randn([32, 1, 256, 256], device=dev)
+th = torch.tensor([[0.97, 0.02, 0.01], [-0.02, 0.98, -0.01]], device=dev).repeat(32, 1, 1).contiguous()
+mg = torch.tensor([9, 9, 9, 9], device=dev, dtype=torch.int32)
+xp32 = torch.randn([32, 512, 33, 33], device=dev)
 for _ in range(a.reps):
+    aug_warp.warp(img, th, mg, pipe._hz_geom_taps, (524, 524))
+    upfirdn2d.upfirdn2d(xp32, f, padding=[1, 1, 1, 1], gain=4)
     conv_igemm.igemm_forward(x256, w256, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     conv_igemm.igemm_forward(x64, w64, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     conv_igemm.igemm_forward(x128, wT, transpose=True, stride=(2, 2), padding=(0, 0), **cfg)
