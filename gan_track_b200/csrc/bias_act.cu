@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(streamk::NTHREADS) bias_act_bulk_kernel(BiasAc
 #pragma unroll
         for (int i = 0; i < L::NP; i++) bfix[i] = L::get(bv, i);
     }
-    auto body = [&](long long e0, Vec16<T>& v0, const Vec16<T>& v1, const Vec16<T>&) {
+    auto body = [&](long long e0, Vec16<T>& v0, const Vec16<T>& v1, const Vec16<T>&, bool live, uint32_t, int) {
+        if (!live) return;
         if (BMODE == 0 || grad != 0 || fixed_b) {
             hot_vector<T, ACT>(v0, v1, bfix, grad, clamp_on, hp);
         } else {
@@ -464,7 +465,8 @@ __global__ void __launch_bounds__(streamk::NTHREADS) bias_act_bwd_bulk_kernel(co
     for (int k = 0; k < VEC; k++) acc[k] = 0.f;
     const hot::Params hp = hot::make_params(alpha, gain, clampv);
     const bool clamp_on = USE_YREF && clampv >= 0.f;
-    auto body = [&](long long, Vec16<T>& v0, const Vec16<T>& v1, const Vec16<T>&) {
+    auto body = [&](long long, Vec16<T>& v0, const Vec16<T>& v1, const Vec16<T>&, bool live, uint32_t, int) {
+        if (!live) return;
         hot_vector<T, ACT>(v0, USE_YREF ? v1 : v0, nullptr, 1, clamp_on, hp);
 #pragma unroll
         for (int k = 0; k < hot::Lanes<T>::NP; k++) {

@@ -22,24 +22,33 @@ constexpr int NT = 256;                 // threads per CTA
 // NIN input streams, S ring stages, CH_BYTES bytes per chunk per stream (a multiple of NT * 16)
 template <int NIN, int S, int CH_BYTES> struct Smem {
     static constexpr int DATA = NIN * S * CH_BYTES;
-    static constexpr int TOTAL = DATA + 2 * S * 8 + 128;   // + barriers + slack for manual 128-byte alignment
+    static constexpr int SIDE = 512;                       // bytes per stage of the optional side stream (e.g. per-pixel noise)
+    static constexpr int TOTAL = DATA + S * SIDE + 2 * S * 8 + 128;   // + side + barriers + slack for manual 128-byte alignment
 };
 
-// f(e0, v0, v1, v2): e0 = global element index of the vector; v0 is updated in place (it becomes the output vector).
+// f(e0, v0, v1, v2, live, side_saddr, vo): e0 = element index of the vector (relative to in0); v0 is updated in place
+// (it becomes the output vector); live = false on lanes past the end of a short last chunk; side_saddr = shared address
+// of this chunk's side-stream bytes; vo = byte offset of the vector inside the chunk.
 // Launch with NTHREADS = NT + 32 threads: warps 0..7 are consumers (thread t < NT owns vectors t, t + NT, ...), warp 8 is
 // the copy-engine driver (one lane).  Consumers never wait on a CTA-wide barrier: per stage there is a `full` mbarrier
 // (load landed) and a `done` mbarrier (all 8 consumer warps have written their results back and fenced them for the
 // async proxy); the driver turns `done` into a bulk store and, once the previous store has drained its buffer, a refill.
 constexpr int NTHREADS = NT + 32;
 
+// Optional side stream: `side` (16-byte aligned) supplies side_full bytes (<= 512, a multiple of 16) per full chunk, e.g.
+// one value per pixel for a chunk that spans CH_BYTES / (C * sizeof(T)) pixels; it is staged next to the chunk and f
+// receives the shared-memory address of its stage.
 template <class T, int NIN, int S, int CH_BYTES, class F>
-__device__ __forceinline__ void run(const T* in0, const T* in1, const T* in2, T* out, long long nelem, uint8_t* smem_raw, F&& f) {
+__device__ __forceinline__ void run(const T* in0, const T* in1, const T* in2, T* out, long long nelem, uint8_t* smem_raw, F&& f,
+                                    const void* side = nullptr, int side_full = 0) {
     using namespace sm100;
     constexpr int VEC = Vec16<T>::N;
     constexpr int VPT = CH_BYTES / 16 / NT;   // vectors per thread per chunk
     static_assert(CH_BYTES % (NT * 16) == 0, "chunk must be a whole number of vectors per thread");
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    uint64_t* full = (uint64_t*)(smem + Smem<NIN, S, CH_BYTES>::DATA);
+    typedef Smem<NIN, S, CH_BYTES> L;
+    uint8_t* sside = smem + L::DATA;
+    uint64_t* full = (uint64_t*)(smem + L::DATA + S * L::SIDE);
     uint64_t* done = full + S;
     const int tid = threadIdx.x;
     const long long total_bytes = (nelem / VEC) * 16;
@@ -64,9 +73,12 @@ __device__ __forceinline__ void run(const T* in0, const T* in1, const T* in2, T*
                 const int stage = (int)(it % S);
                 const long long off = c * CH_BYTES;
                 const uint32_t bytes = (uint32_t)((total_bytes - off) < CH_BYTES ? (total_bytes - off) : CH_BYTES);
-                mbar_arrive_expect_tx(&full[stage], bytes * NIN);
+                // side bytes of a short last chunk scale with it (both are whole pixels)
+                const uint32_t sbytes = side ? (uint32_t)(((long long)bytes * side_full) / CH_BYTES) : 0u;
+                mbar_arrive_expect_tx(&full[stage], bytes * NIN + sbytes);
 #pragma unroll
                 for (int k = 0; k < NIN; k++) bulk_load(smem + (k * S + stage) * CH_BYTES, src[k] + off, bytes, &full[stage]);
+                if (sbytes) bulk_load(sside + stage * L::SIDE, (const uint8_t*)side + c * side_full, sbytes, &full[stage]);
             };
             for (int it = 0; it < S; it++) issue(it);
             long long it = 0;
@@ -98,6 +110,9 @@ __device__ __forceinline__ void run(const T* in0, const T* in1, const T* in2, T*
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
             const int vo = (tid + j * NT) * 16;
+            *reinterpret_cast<uint4*>(v0[j].v) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(v1[j].v) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(v2[j].v) = make_uint4(0, 0, 0, 0);
             if (vo < bytes) {
                 *reinterpret_cast<uint4*>(v0[j].v) = lds128(sa + stage * CH_BYTES + vo);
                 if (NIN > 1) *reinterpret_cast<uint4*>(v1[j].v) = lds128(sa + (1 * S + stage) * CH_BYTES + vo);
@@ -107,10 +122,9 @@ __device__ __forceinline__ void run(const T* in0, const T* in1, const T* in2, T*
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
             const int vo = (tid + j * NT) * 16;
-            if (vo < bytes) {
-                f((off + vo) / (long long)sizeof(T), v0[j], v1[j], v2[j]);
-                sts128(sa + stage * CH_BYTES + vo, *reinterpret_cast<const uint4*>(v0[j].v));
-            }
+            const bool live = vo < bytes;     // f runs on every lane (it may use warp shuffles); dead lanes hold garbage
+            f((off + vo) / (long long)sizeof(T), v0[j], v1[j], v2[j], live, sa + (uint32_t)(L::DATA + stage * L::SIDE), vo);
+            if (live) sts128(sa + stage * CH_BYTES + vo, *reinterpret_cast<const uint4*>(v0[j].v));
         }
         fence_proxy_async();
         __syncwarp();

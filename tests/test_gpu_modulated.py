@@ -32,7 +32,9 @@ def _ref_demod_act(x, d, noise, b, act, gain, clamp):
     return bias_act.bias_act(x, b.to(x.dtype) if b is not None else None, act=act, gain=gain, clamp=clamp)
 
 
-SHAPES = [(4, 64, 16, 16), (2, 512, 8, 8), (3, 128, 9, 7), (2, 256, 5, 5)]
+SHAPES = [(4, 64, 16, 16), (2, 512, 8, 8), (3, 128, 9, 7), (2, 256, 5, 5),
+          # >= 1 MB per sample: the bulk-copy staged kernels (csrc/stream_bulk.cuh), incl. a short last chunk and C/VEC > 32
+          (2, 64, 128, 128), (2, 128, 64, 72), (1, 256, 64, 64), (1, 512, 40, 32)]
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
