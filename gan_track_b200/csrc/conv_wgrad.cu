@@ -24,6 +24,18 @@
 
 using namespace sm100;
 
+// conv_wgrad_halo.cu: halo-staged, tap-paired kernel for the stride-1 3x3 layers
+bool gt_wgrad_halo_applicable(int N, int UH, int UW, int UC, int SC, int SH, int SW, int KH, int KW, int stride, int pad);
+long long gt_wgrad_halo_workspace(int N, int UH, int UW, int UC, int SC);
+int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n, long long ss_h,
+                         long long ss_w, int SH, int SW, int SC, int N, int pad, float* workspace, long long workspace_floats, cudaStream_t stream);
+static int g_wgrad_variant = 0;   // 0 = auto (halo kernel where it applies), 1 = per-tap-row kernel only
+extern "C" int gt_conv_wgrad_config(int variant) {
+    const int old = g_wgrad_variant;
+    g_wgrad_variant = variant;
+    return old;
+}
+
 namespace {
 
 constexpr int WM = 128;        // U channels per tile (UMMA M)
@@ -248,7 +260,12 @@ int launch_wgrad(const CUtensorMap& tmU, const CUtensorMap& tmS, const WgradPara
 extern "C" long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW) {
     if (N <= 0 || UH <= 0 || UW <= 0 || UC <= 0 || SC <= 0 || KH <= 0 || KW <= 0) return 0;
     WgradPlan pl = make_plan(N, UH, UW, UC, SC, KH * KW);
-    return (long long)pl.splits * KH * KW * UC * SC;
+    long long need = (long long)pl.splits * KH * KW * UC * SC;
+    if (KH == 3 && KW == 3 && UC % 64 == 0 && SC % 64 == 0) {           // the halo kernel may take the call: cover its plan too
+        const long long h = gt_wgrad_halo_workspace(N, UH, UW, UC, SC);
+        if (h > need) need = h;
+    }
+    return need;
 }
 
 extern "C" int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n,
@@ -265,6 +282,17 @@ extern "C" int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h
     GT_REQUIRE(us_w % 8 == 0 && us_h % 8 == 0 && us_n % 8 == 0 && ss_w % 8 == 0 && ss_h % 8 == 0 && ss_n % 8 == 0,
                "gt_conv2d_wgrad_f16: strides must be multiples of 8 elements");
     const int ntaps = KH * KW;
+    if (g_wgrad_variant == 0 && gt_wgrad_halo_applicable(N, UH, UW, UC, SC, SH, SW, KH, KW, stride, pad)) {
+        const int splits = gt_launch_wgrad_halo(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, pad, workspace, workspace_floats,
+                                                (cudaStream_t)stream);
+        if (splits <= 0) return GT_ERR_CUDA;
+        const long long per = (long long)ntaps * UC * SC;
+        long long g = (per + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        wgrad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, splits, ntaps, UC, SC, KW, (__half*)dw, ds_u, ds_s, ds_r, ds_c);
+        GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
+        return GT_OK;
+    }
     WgradPlan pl = make_plan(N, UH, UW, UC, SC, ntaps);
     GT_REQUIRE(workspace_floats >= (long long)pl.splits * ntaps * UC * SC, "gt_conv2d_wgrad_f16: workspace too small");
 

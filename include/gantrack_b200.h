@@ -104,6 +104,9 @@ int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long
  * ds_r / ds_c.  Split-K partial sums go through `workspace` (fp32, at least gt_conv2d_wgrad_workspace(...) floats) and
  * are reduced in a fixed order, so the result is deterministic. */
 long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW);
+/* Kernel selection for gt_conv2d_wgrad_f16: 0 = automatic (halo-staged tap-paired kernel for stride-1 3x3, per-tap-row
+ * kernel otherwise), 1 = per-tap-row kernel only.  Returns the previous value. */
+int gt_conv_wgrad_config(int variant);
 int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s,
                         long long ss_n, long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride,
                         int pad, void* dw, long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace,

@@ -25,6 +25,12 @@ CASES = [
     ('3x3_T_s2_64_64_128', 1, 64, 64, 128, 128, 3, 2, 0, True),
     ('3x3_T_s1_p1_64_128_32', 2, 64, 128, 32, 32, 3, 1, 1, True),
     ('3x3_T_s1_p0_64_64_16', 2, 64, 64, 16, 16, 3, 1, 0, True),
+    # stride-1 3x3 with enough pixels for the halo-staged tap-paired wgrad kernel (csrc/conv_wgrad_halo.cu), incl. ragged tiles
+    ('3x3_p1_64_64_128_n8', 8, 64, 64, 128, 128, 3, 1, 1, False),
+    ('3x3_p1_128_64_72x64', 4, 128, 64, 72, 64, 3, 1, 1, False),
+    ('3x3_T_s1_p1_64_128_40', 6, 64, 128, 40, 40, 3, 1, 1, True),
+    ('3x3_p0_64_64_66', 4, 64, 64, 66, 66, 3, 1, 0, False),
+    ('3x3_p1_256_256_32_n8', 8, 256, 256, 32, 32, 3, 1, 1, False),
 ]
 
 
@@ -78,6 +84,14 @@ def test_igemm_wgrad_matches_torch(case):
     # deterministic: the split-K reduction has a fixed order
     dw2 = conv_igemm.igemm_wgrad(dy, x, tuple(w.shape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
     assert torch.equal(dw, dw2)
+    # the per-tap-row kernel and the halo-staged tap-paired kernel agree (same products, different summation split)
+    from gan_track_b200 import _lib
+    old_v = _lib.load().gt_conv_wgrad_config(1)
+    try:
+        dw3 = conv_igemm.igemm_wgrad(dy, x, tuple(w.shape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
+    finally:
+        _lib.load().gt_conv_wgrad_config(old_v)
+    assert _rel(dw3, ref) <= TOL and _rel(dw, dw3) <= TOL
 
 
 def test_igemm_linearity_and_adjointness_full_size():

@@ -44,6 +44,11 @@ CASES = [
     ('1x1 128->256 64x64', 2, 128, 256, 64, 64, 1, 1, 0, False),
     ('3x3 T s2 128->64 32x32', 2, 128, 64, 32, 32, 3, 2, 0, True),
     ('3x3 T s2 256->128 64x64', 1, 256, 128, 64, 64, 3, 2, 0, True),
+    ('3x3 p1 64->64 128x128 n8', 8, 64, 64, 128, 128, 3, 1, 1, False),
+    ('3x3 p1 128->64 72x64 n4', 4, 128, 64, 72, 64, 3, 1, 1, False),
+    ('3x3 T s1 p1 64->128 40x40 n6', 6, 64, 128, 40, 40, 3, 1, 1, True),
+    ('3x3 p0 64->64 66x66 n4', 4, 64, 64, 66, 66, 3, 1, 0, False),
+    ('3x3 p1 256->256 32x32 n8', 8, 256, 256, 32, 32, 3, 1, 1, False),
 ]
 
 
