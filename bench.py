@@ -180,38 +180,112 @@ def cpu_baseline_sample(res, cbase, aug, batch=4):
 
 # ------------------------------------------------------------------------------------------------ our arm
 
-def dominant_kernel_roofline(device, pk):
-    """Roofline of the dominant kernel of OUR launches, timed live with CUDA events on the launching stream, L2 flushed
-    between launches.  See DESIGN.md 'Measurement' for the algorithmic bytes/flops per launch."""
-    from gan_track_b200.torch_utils.ops import bias_act
-    traffic = None
+# The kernel with the largest share of the step's GPU time in the committed step profile (profiles/r01_step_profile.txt);
+# `roofline` reports this one, `roofline_all` every hot kernel measured the same way.
+DOMINANT = 'conv_igemm_halo fwd 3x3 64->64 @256x256'
+
+
+def hot_kernel_rooflines(device, pk):
+    """Rooflines of OUR hot kernels at their training shapes (batch 32 of the 256x256 config), timed live with CUDA
+    events on the launching stream.  Cold caches without an interfering flush: each case rotates over enough distinct
+    input/output buffer sets that consecutive launches never touch the same memory within 2x the 126 MB L2, and a batch
+    of launches is timed back to back (sustained figure; the denominators are MEASURED_PEAKS.json's HBM copy bandwidth
+    and bf16 burst throughput).  Algorithmic bytes / flops per launch: DESIGN.md section 3."""
+    from gan_track_b200.torch_utils.ops import bias_act, conv_igemm, modulated, upfirdn2d
+    traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get('bias_act_fwd_f16_32x64x256x256')
+                traffic = json.load(f)
         except Exception:
-            traffic = None
-    x = torch.randn([32, 64, 256, 256], device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
-    b = torch.randn([64], device=device, dtype=torch.float16)
-    flush = torch.empty([256 << 20], dtype=torch.uint8, device=device)
-    for _ in range(3):
-        bias_act.bias_act(x, b, act='lrelu', clamp=256.0)
-    times = []
-    for _ in range(10):
-        flush.zero_()
+            traffic = {}
+    cl = torch.channels_last
+    L2 = 126 << 20
+
+    def rot(make, nbytes_per_set):
+        n = max(2, int(np.ceil(2 * L2 / max(nbytes_per_set, 1))) + 1)
+        return [make() for _ in range(min(n, 12))]
+
+    def t16(shape):
+        return torch.randn(shape, device=device).to(torch.float16).contiguous(memory_format=cl)
+
+    def timeit(fns, iters=24):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        bias_act.bias_act(x, b, act='lrelu', clamp=256.0)
+        for i in range(iters):
+            fns[i % len(fns)]()
         e.record()
         e.synchronize()
-        times.append(s.elapsed_time(e))
-    ms = float(np.mean(times))
-    nbytes = 2 * x.numel() * 2
-    achieved = nbytes / (ms * 1e-3) / 1e9
-    return {'kernel': 'bias_act_vec_kernel<half, lrelu> fwd [32,64,256,256] channels-last', 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'],
-            'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'], 'traffic': traffic, 'peak_source': pk['src'], 'ms_per_launch': ms,
-            'algorithmic_bytes_per_launch': nbytes}
+        return s.elapsed_time(e) / iters
+
+    out = {}
+
+    def add(name, kernel, bound, work, ms):
+        if bound == 'tensor':
+            achieved, peak, unit = work / (ms * 1e-3) / 1e12, pk['tflops'], 'TFLOP/s'
+            extra = {'algorithmic_flops_per_launch': work}
+        else:
+            achieved, peak, unit = work / (ms * 1e-3) / 1e9, pk['hbm_gbs'], 'GB/s'
+            extra = {'algorithmic_bytes_per_launch': work}
+        out[name] = dict(kernel=kernel, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=traffic.get(name),
+                         peak_source=pk['src'], ms_per_launch=ms, **extra)
+
+    cfg = dict(output_padding=(0, 0), groups=1, stride=(1, 1), padding=(1, 1))
+    for ci, co, r, tag in [(512, 512, 32, 'conv_igemm_halo_kernel<256,2,4,1>'), (256, 256, 64, 'conv_igemm_halo_kernel<256,1,5,2>'),
+                           (128, 128, 128, 'conv_igemm_halo_kernel<128,2,6,2>'), (64, 64, 256, 'conv_igemm_halo_kernel<64,4,6,2>')]:
+        xs = rot(lambda: t16([32, ci, r, r]), 32 * ci * r * r * 2 * 2)
+        w = (torch.randn([co, ci, 3, 3], device=device) / (ci * 9) ** 0.5).to(torch.float16)
+        pkd = conv_igemm.pack_weight(w, False)
+        fl = 2.0 * 32 * r * r * ci * co * 9
+        ms = timeit([lambda x=x: conv_igemm.igemm_forward(x, w, transpose=False, packed=pkd, **cfg) for x in xs])
+        add(f'conv_igemm_halo fwd 3x3 {ci}->{co} @{r}x{r}', tag, 'tensor', fl, ms)
+        ms = timeit([lambda x=x: conv_igemm.igemm_wgrad(x, x, (co, ci, 3, 3), transpose=False, **cfg) for x in xs])
+        add(f'conv_wgrad_halo 3x3 {ci}x{co} over 32x{r}x{r} pixels', 'conv_wgrad_halo_kernel + wgrad_reduce_kernel', 'tensor', fl, ms)
+        del xs
+
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], device=device)
+    xs = rot(lambda: t16([32, 64, 257, 257]), 32 * 64 * 257 * 257 * 4)
+    ms = timeit([lambda x=x: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4) for x in xs])
+    add('upfirdn2d 4x4 blur [32,64,257,257]->[32,64,256,256] f16 NHWC', 'upfirdn2d_tma_kernel<half>', 'hbm', (32 * 64 * 257 * 257 + 32 * 64 * 256 * 256) * 2, ms)
+    del xs
+
+    shape = [32, 64, 256, 256]
+    nb = 32 * 64 * 256 * 256 * 2
+    xs = rot(lambda: t16(shape), 2 * nb)
+    b = torch.randn([64], device=device, dtype=torch.float16)
+    ms = timeit([lambda x=x: bias_act.bias_act(x, b, act='lrelu', clamp=256.0) for x in xs])
+    add('bias_act fwd lrelu [32,64,256,256] f16 NHWC', 'bias_act_bulk_kernel<half,lrelu>', 'hbm', 2 * nb, ms)
+    lib = _lib_handle()
+    ws = torch.empty([lib.gt_bias_act_bwd_workspace(32 * 256 * 256, 64, 1)], dtype=torch.float32, device=device)
+    db = torch.empty([64], dtype=torch.float32, device=device)
+    outs = [torch.empty_like(x) for x in xs]
+    from gan_track_b200 import _lib
+
+    def bwd(i):
+        dy, y, dx = xs[i], xs[(i + 1) % len(xs)], outs[i]
+        _lib.check(lib.gt_bias_act_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), _lib.ptr(db), _lib.ptr(ws), ws.numel(), 1, 3, 0.2, float(np.sqrt(2)), 256.0,
+                                       32 * 256 * 256, 64, 1, _lib.stream_of(dy)), 'gt_bias_act_bwd')
+    ms = timeit([lambda i=i: bwd(i) for i in range(len(xs))])
+    add('bias_act bwd (dx + db) [32,64,256,256] f16 NHWC', 'bias_act_bwd_bulk_kernel<half,lrelu> + reduce_partials_kernel', 'hbm', 3 * nb, ms)
+    del outs
+    sm = torch.randn([32, 64], device=device)
+    dm = torch.rand([32, 64], device=device)
+    nz = torch.randn([32, 1, 256, 256], device=device).to(torch.float16)
+    ms = timeit([lambda x=x: modulated.mod_scale(x, sm) for x in xs])
+    add('mod_scale fwd [32,64,256,256] f16 NHWC', 'mod_scale_fwd_bulk_kernel<half>', 'hbm', 2 * nb, ms)
+    ms = timeit([lambda x=x: modulated.demod_act(x, dm, nz, b, act='lrelu', gain=float(np.sqrt(2)), clamp=256.0) for x in xs])
+    add('demod_act fwd [32,64,256,256] f16 NHWC', 'demod_act_fwd_bulk_kernel<half,lrelu>', 'hbm', 2 * nb, ms)
+    del xs
+    return out
+
+
+def _lib_handle():
+    from gan_track_b200 import _lib
+    return _lib.load()
 
 
 def run_ours(args):
@@ -276,11 +350,14 @@ def run_ours(args):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.profile_range:
         torch.cuda.profiler.start()
+    trainer.time_phases = True
     s.record()
     for _ in range(args.steps):
         trainer.train_step(dev_img, dev_c)
     e.record()
     barrier()
+    phase_ms = {k: {'replays': n, 'ms': round(t, 3)} for k, (n, t) in trainer.phase_times().items()}
+    trainer.time_phases = False
     if args.profile_range:
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
@@ -313,7 +390,8 @@ def run_ours(args):
         trainer.check_consistency()
 
     pk = peaks()
-    roof = dominant_kernel_roofline(device, pk) if rank == 0 else None
+    roof_all = hot_kernel_rooflines(device, pk) if rank == 0 else None
+    roof = dict(roof_all[DOMINANT], case=DOMINANT) if roof_all else None
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -331,8 +409,8 @@ def run_ours(args):
                                    f'lazy R1 (every 16) + path-length (every 4), ADA={args.aug}', 'global_batch': global_batch, 'batch_gpu': batch_gpu,
                        'parallelism': f'dp{world}', 'phase_counts_in_timed_region': phase_counts,
                        'l2_policy': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush in the step loop',
-                       'conv_routes': conv_stats, 'cuda_graphs': not args.no_graphs},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base,
+                       'conv_routes': conv_stats, 'cuda_graphs': not args.no_graphs, 'phase_ms': phase_ms},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base, 'roofline_all': roof_all,
         }
         if flops_per_img:
             line['model_tflops'] = value * 1000 * flops_per_img / 1e12

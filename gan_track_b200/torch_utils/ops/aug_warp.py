@@ -1,5 +1,6 @@
 """Fused geometric resampling of the ADA pipe: reflect-pad -> 2x upsample (separable low-pass) -> bilinear
-`grid_sample` on an affine grid, as ONE kernel with device-resident margins (csrc/augment_warp.cu).
+`grid_sample` on an affine grid with device-resident margins (csrc/augment_warp.cu): two passes through a workspace
+(separable upsampling, then 4-tap resampling), or one 49-tap gather kernel when `two_pass` is off.
 
 Replaces the op sequence of S3/training/augment_mi.py:303-318 (F.pad 'reflect', upfirdn2d.upsample2d,
 F.affine_grid, grid_sample_gradfix.grid_sample) without the device->host read of the margins (:299).
@@ -12,13 +13,22 @@ import torch
 from ... import _lib
 
 
+two_pass = True      # False: the single 49-tap gather kernel (no workspace)
+
+
 def _call(fn_name, src, theta, margins, taps, dst, B, C, H, W, OH, OW):
     lib = _lib.load()
     arr = (ctypes.c_float * len(taps))(*taps)
     with torch.cuda.device(src.device):
+        ws, nws = None, 0
+        if two_pass:
+            # the 2x-upsampled image (or its gradient) at the largest possible margins; only the part the actual margins
+            # need is touched
+            nws = lib.gt_aug_warp_workspace(B, C, H, W)
+            ws = torch.empty([nws], dtype=torch.float32, device=src.device)
         _lib.check(getattr(lib, fn_name)(_lib.ptr(src), _lib.ptr(theta), _lib.ptr(margins), arr, len(taps), _lib.ptr(dst), B, C, H, W, OH, OW,
-                                         _lib.stream_of(src)), fn_name)
-    _lib.count_launch()
+                                         _lib.ptr(ws), nws, _lib.stream_of(src)), fn_name)
+    _lib.count_launch((2 if fn_name == 'gt_aug_warp_fwd' else 3) if two_pass else 1)
 
 
 def _check(theta, margins, B):

@@ -233,6 +233,8 @@ class Trainer:
                 self.phases.append(dnnlib.EasyDict(name=name + 'reg', module=module, opt=opt, interval=reg_interval, reducer=reducer, grad_set=None))
         self.cur_nimg = 0
         self.batch_idx = 0
+        self.time_phases = False          # bench.py: CUDA-event time of every graphed phase replay (read with phase_times())
+        self._phase_events = []
         self.phase_counts = {p.name: 0 for p in self.phases}
         for ph in self.phases:
             ph.update(graphs=None, static=None, eager_runs=0, replay_counts=None)
@@ -368,14 +370,31 @@ class Trainer:
             _lib.launches = launches0
             conv_backend.stats.update(conv0)
         ga, gb = phase.graphs
+        ev = None
+        if self.time_phases:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         ga.replay()
         if gb is not None:
             torch.distributed.all_reduce(st.flat)
             gb.replay()
+        if ev is not None:
+            ev[1].record()
+            self._phase_events.append((phase.name, ev))
         n, routes = phase.replay_counts
         _lib.launches += n
         for k, v in routes.items():
             conv_backend.stats[k] += v
+
+    def phase_times(self):
+        """{phase: (replays, mean ms)} of the replays recorded since `time_phases` was switched on (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        acc = {}
+        for name, (a, b) in self._phase_events:
+            n, t = acc.get(name, (0, 0.0))
+            acc[name] = (n + 1, t + a.elapsed_time(b))
+        self._phase_events = []
+        return {k: (n, t / n) for k, (n, t) in acc.items()}
 
     def check_consistency(self):
         for module in (self.G, self.D):

@@ -113,15 +113,20 @@ int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long
                         long long workspace_floats, void* stream);
 
 /* ---- ADA geometric warp (fp32) ------------------------------------------------------------------------------------
- * One gather kernel for S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps, up=2)
- * -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE
- * int[4] (mx0, my0, mx1, my1), so the host never reads it back (the reference syncs at :299).  `taps_host` is a HOST
- * array of ntaps normalised low-pass taps (even, <= 12; sym6 on the path).  x: [B,C,H,W], y: [B,C,OH,OW], theta: [B,2,3].
- * gt_aug_warp_bwd is the adjoint (gx is zeroed, then accumulated with atomicAdd). */
+ * Replaces the op sequence of S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps,
+ * up=2) -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE
+ * int[4] (mx0, my0, mx1, my1), each in [0, W-1] / [0, H-1], so the host never reads it back (the reference syncs at :299).
+ * `taps_host` is a HOST array of ntaps normalised low-pass taps (even, <= 12; sym6 on the path).  x: [B,C,H,W],
+ * y: [B,C,OH,OW], theta: [B,2,3].
+ * With `workspace` (fp32, at least gt_aug_warp_workspace(B,C,H,W) floats: the 2x-upsampled image at the largest margins)
+ * the call runs as two passes -- separable upsampling of the reflect-padded image into the workspace, then the 4-tap
+ * bilinear resampling; with workspace == NULL as one 49-tap gather kernel.  gt_aug_warp_bwd is the adjoint (gx is
+ * zeroed, then accumulated with atomicAdd; the workspace holds the gradient of the upsampled image). */
+long long gt_aug_warp_workspace(int B, int C, int H, int W);
 int gt_aug_warp_fwd(const float* x, const float* theta, const int* margins, const float* taps_host, int ntaps, float* y, int B,
-                    int C, int H, int W, int OH, int OW, void* stream);
+                    int C, int H, int W, int OH, int OW, float* workspace, long long workspace_floats, void* stream);
 int gt_aug_warp_bwd(const float* gy, const float* theta, const int* margins, const float* taps_host, int ntaps, float* gx, int B,
-                    int C, int H, int W, int OH, int OW, void* stream);
+                    int C, int H, int W, int OH, int OW, float* workspace, long long workspace_floats, void* stream);
 
 /* ---- fused element-wise halves of the training-mode modulated convolution (channels-last [N, P = H*W, C]) ------------
  * Replace the torch op sequences of S3/training/networks_stylegan2.py:69 (x * styles), :71-72 (fma with the demodulation

@@ -8,6 +8,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[True, False], ids=['two_pass', 'single_gather'], autouse=True)
+def warp_mode(request):
+    """Every test runs with both forms of the fused warp: two passes through a workspace (default) and the single gather."""
+    from gan_track_b200.torch_utils.ops import aug_warp
+    old = aug_warp.two_pass
+    aug_warp.two_pass = request.param
+    yield request.param
+    aug_warp.two_pass = old
+
+
 def _pipe(**kw):
     from gan_track_b200.training import augment
     base = dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1)
