@@ -449,6 +449,114 @@ int bulk_bands(int N, long long P, int C, int esz, int ch_bytes, int max_bands) 
     return (int)bands;
 }
 
+
+// =====================================================================================================================
+// Second-order passes (the path-length regulariser differentiates the generator's backward, S3/training/loss.py:85-100):
+// the derivatives of gt_mod_scale_bwd / gt_demod_act_bwd with respect to their inputs, each as ONE pass instead of the
+// ~10 element-wise torch passes the formulas take when written with tensor ops.  Same band / row-group structure as the
+// first-order direct kernels; per-(n, c) reductions go through the same partial-sum workspace.
+//   mod_scale:   d_gy = ggx * s + ggs * x        d_x = ggs * gy                 d_s[n,c] = sum_hw ggx * gy
+//   demod_act:   m = gain * act'(y) * [|y| < clamp],  g1 = gy * m
+//                d_gy = m * (ggx * d + ggd * x + ggnz + ggs0)      d_x = ggd * g1      d_d[n,c] = sum_hw ggx * g1
+// Any of ggx / ggs / ggd / ggnz / ggs0 may be NULL (that cotangent is absent); outputs that are not wanted are NULL.
+// =====================================================================================================================
+template <class T>
+__global__ void __launch_bounds__(256) mod_scale_bwd2_kernel(const T* __restrict__ ggx, const float* __restrict__ ggs, const T* __restrict__ gy,
+                                                             const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ d_gy,
+                                                             T* __restrict__ d_x, float* __restrict__ partial, int C, long long P) {
+    constexpr int VEC = Vec16<T>::N;
+    __shared__ float red[256 * VEC];
+    const BandGeom g = band_geom<VEC>(C);
+    const int band = blockIdx.x, bands = gridDim.x, n = blockIdx.y;
+    float acc[MAXJ][VEC];
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[j][k] = 0.f;
+    const long long base = (long long)n * P * C;
+    for (long long p = band + (long long)bands * g.rg; p < P; p += (long long)bands * g.rgroups) {
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++) {
+            const int cv = g.lane + g.lanes * j;
+            if (j < g.nj && cv < g.cvecs) {
+                const long long e = base + p * C + (long long)cv * VEC;
+                Vec16<T> av, gv, xv, o1, o2;
+                if (ggx) av = ld16_stream(ggx + e);
+                if (ggx || d_x) gv = ld16_stream(gy + e);
+                if (ggs && d_gy) xv = ld16_stream(x + e);
+                const float* sp = s + (long long)n * C + cv * VEC;
+                const float* gsp = ggs ? ggs + (long long)n * C + cv * VEC : nullptr;
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    const float a = ggx ? (float)to_acc<T>(av.v[k]) : 0.f;
+                    const float gsv = gsp ? (float)to_acc<T>(from_acc<T>(gsp[k])) : 0.f;
+                    float t = 0.f;
+                    if (ggx) t += a * (float)to_acc<T>(from_acc<T>(sp[k]));
+                    if (gsp && d_gy) t += gsv * (float)to_acc<T>(xv.v[k]);
+                    o1.v[k] = from_acc<T>(t);
+                    if (d_x) o2.v[k] = from_acc<T>(gsv * (float)to_acc<T>(gv.v[k]));
+                    if (ggx) acc[j][k] += a * (float)to_acc<T>(gv.v[k]);
+                }
+                if (d_gy) st16_stream(d_gy + e, o1);
+                if (d_x) st16_stream(d_x + e, o2);
+            }
+        }
+    }
+    if (partial) write_partial<VEC>(g, acc, red, partial + ((long long)n * bands + band) * C, C);
+}
+
+template <class T, int ACT>
+__global__ void __launch_bounds__(256) demod_act_bwd2_kernel(const T* __restrict__ ggx, const float* __restrict__ ggd, const T* __restrict__ ggnz,
+                                                             const float* __restrict__ ggs0, const T* __restrict__ gy, const T* __restrict__ yref,
+                                                             const T* __restrict__ x, const float* __restrict__ d, T* __restrict__ d_gy,
+                                                             T* __restrict__ d_x, float* __restrict__ partial, int C, long long P, float alpha,
+                                                             float gain, float clampv) {
+    constexpr int VEC = Vec16<T>::N;
+    __shared__ float red[256 * VEC];
+    const BandGeom g = band_geom<VEC>(C);
+    const int band = blockIdx.x, bands = gridDim.x, n = blockIdx.y;
+    float acc[MAXJ][VEC];
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[j][k] = 0.f;
+    const long long base = (long long)n * P * C;
+    const bool need_x = (ggd != nullptr) && (d_gy != nullptr);
+    for (long long p = band + (long long)bands * g.rg; p < P; p += (long long)bands * g.rgroups) {
+        const float nzv = ggnz ? (float)to_acc<T>(ggnz[(long long)n * P + p]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++) {
+            const int cv = g.lane + g.lanes * j;
+            if (j < g.nj && cv < g.cvecs) {
+                const long long e = base + p * C + (long long)cv * VEC;
+                Vec16<T> av, gv, yv, xv, o1, o2;
+                if (ggx) av = ld16_stream(ggx + e);
+                gv = ld16_stream(gy + e);
+                yv = ld16_stream(yref + e);
+                if (need_x) xv = ld16_stream(x + e);
+                const long long nc = (long long)n * C + cv * VEC;
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    const float m = act_slope<ACT>((float)to_acc<T>(yv.v[k]), alpha, gain, clampv);
+                    const float a = ggx ? (float)to_acc<T>(av.v[k]) : 0.f;
+                    const float gdv = ggd ? (float)to_acc<T>(from_acc<T>(ggd[nc + k])) : 0.f;
+                    const float g1 = (float)to_acc<T>(from_acc<T>((float)to_acc<T>(gv.v[k]) * m));   // materialised in T like the first-order pass
+                    float t = nzv;
+                    if (ggx) t += d ? a * (float)to_acc<T>(from_acc<T>(d[nc + k])) : a;
+                    if (need_x) t += gdv * (float)to_acc<T>(xv.v[k]);
+                    if (ggs0) t += (float)to_acc<T>(from_acc<T>(ggs0[nc + k]));
+                    o1.v[k] = from_acc<T>(m * t);
+                    if (d_x) o2.v[k] = from_acc<T>(gdv * g1);
+                    if (partial) acc[j][k] += a * g1;
+                }
+                if (d_gy) st16_stream(d_gy + e, o1);
+                if (d_x) st16_stream(d_x + e, o2);
+            }
+        }
+    }
+    if (partial) write_partial<VEC>(g, acc, red, partial + ((long long)n * bands + band) * C, C);
+}
+
 // out[n][c] = sum over bands (in order) of partial[n][band][c]
 __global__ void band_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int NC_n, int C, int bands) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,5 +783,59 @@ extern "C" int gt_demod_act_bwd(const void* gy, const void* yref, const void* x,
     }
     band_reduce_kernel<<<rgrid, 256, 0, st>>>(p0, s0, N, C, bands);
     GT_CUDA_LAUNCH_CHECK("gt_demod_act_bwd(reduce s0)");
+    return GT_OK;
+}
+
+extern "C" int gt_mod_scale_bwd2(const void* ggx, const float* ggs, const void* gy, const void* x, const float* s, void* d_gy, void* d_x, float* d_s,
+                                 float* workspace, long long workspace_floats, int dtype, int N, long long P, int C, void* stream) {
+    GT_REQUIRE(gy && x && s && workspace, "gt_mod_scale_bwd2: null pointer");
+    GT_REQUIRE(d_s == nullptr || ggx != nullptr, "gt_mod_scale_bwd2: d_s needs ggx");
+    GT_REQUIRE(d_x == nullptr || ggs != nullptr, "gt_mod_scale_bwd2: d_x needs ggs");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    GT_REQUIRE((dtype == GT_F16 && shape_ok<__half>(N, P, C)) || (dtype == GT_F32 && shape_ok<float>(N, P, C)), "gt_mod_scale_bwd2: unsupported shape N=%d P=%lld C=%d",
+               N, P, C);
+    const int bands = pick_bands(N, P, C, vec);
+    GT_REQUIRE((long long)N * bands * C <= workspace_floats, "gt_mod_scale_bwd2: workspace too small");
+    dim3 grid(bands, N);
+    float* part = d_s ? workspace : nullptr;
+    GT_MOD_DISPATCH((mod_scale_bwd2_kernel<float><<<grid, 256, 0, st>>>((const float*)ggx, ggs, (const float*)gy, (const float*)x, s, (float*)d_gy, (float*)d_x, part, C, P)),
+                    (mod_scale_bwd2_kernel<__half><<<grid, 256, 0, st>>>((const __half*)ggx, ggs, (const __half*)gy, (const __half*)x, s, (__half*)d_gy, (__half*)d_x, part, C, P)));
+    GT_CUDA_LAUNCH_CHECK("gt_mod_scale_bwd2");
+    if (d_s) {
+        band_reduce_kernel<<<(int)(((long long)N * C + 255) / 256), 256, 0, st>>>(workspace, d_s, N, C, bands);
+        GT_CUDA_LAUNCH_CHECK("gt_mod_scale_bwd2(reduce)");
+    }
+    return GT_OK;
+}
+
+extern "C" int gt_demod_act_bwd2(const void* ggx, const float* ggd, const void* ggnz, const float* ggs0, const void* gy, const void* yref, const void* x,
+                                 const float* d, void* d_gy, void* d_x, float* d_d, float* workspace, long long workspace_floats, int dtype, int act,
+                                 float alpha, float gain, float clamp, int N, long long P, int C, void* stream) {
+    GT_REQUIRE(gy && yref && workspace, "gt_demod_act_bwd2: null pointer");
+    GT_REQUIRE(act == A_LINEAR || act == A_LRELU, "gt_demod_act_bwd2: only linear (1) and lrelu (3) are supported; got %d", act);
+    GT_REQUIRE(d_d == nullptr || (ggx != nullptr && d != nullptr), "gt_demod_act_bwd2: d_d needs ggx and d");
+    GT_REQUIRE(d_x == nullptr || ggd != nullptr, "gt_demod_act_bwd2: d_x needs ggd");
+    GT_REQUIRE(ggd == nullptr || x != nullptr || d_gy == nullptr, "gt_demod_act_bwd2: ggd needs x");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = dtype == GT_F16 ? 8 : 4;
+    GT_REQUIRE((dtype == GT_F16 && shape_ok<__half>(N, P, C)) || (dtype == GT_F32 && shape_ok<float>(N, P, C)), "gt_demod_act_bwd2: unsupported shape N=%d P=%lld C=%d",
+               N, P, C);
+    const int bands = pick_bands(N, P, C, vec);
+    GT_REQUIRE((long long)N * bands * C <= workspace_floats, "gt_demod_act_bwd2: workspace too small");
+    dim3 grid(bands, N);
+    float* part = d_d ? workspace : nullptr;
+    if (act == A_LRELU) {
+        GT_MOD_DISPATCH((demod_act_bwd2_kernel<float, A_LRELU><<<grid, 256, 0, st>>>((const float*)ggx, ggd, (const float*)ggnz, ggs0, (const float*)gy, (const float*)yref, (const float*)x, d, (float*)d_gy, (float*)d_x, part, C, P, alpha, gain, clamp)),
+                        (demod_act_bwd2_kernel<__half, A_LRELU><<<grid, 256, 0, st>>>((const __half*)ggx, ggd, (const __half*)ggnz, ggs0, (const __half*)gy, (const __half*)yref, (const __half*)x, d, (__half*)d_gy, (__half*)d_x, part, C, P, alpha, gain, clamp)));
+    } else {
+        GT_MOD_DISPATCH((demod_act_bwd2_kernel<float, A_LINEAR><<<grid, 256, 0, st>>>((const float*)ggx, ggd, (const float*)ggnz, ggs0, (const float*)gy, (const float*)yref, (const float*)x, d, (float*)d_gy, (float*)d_x, part, C, P, alpha, gain, clamp)),
+                        (demod_act_bwd2_kernel<__half, A_LINEAR><<<grid, 256, 0, st>>>((const __half*)ggx, ggd, (const __half*)ggnz, ggs0, (const __half*)gy, (const __half*)yref, (const __half*)x, d, (__half*)d_gy, (__half*)d_x, part, C, P, alpha, gain, clamp)));
+    }
+    GT_CUDA_LAUNCH_CHECK("gt_demod_act_bwd2");
+    if (d_d) {
+        band_reduce_kernel<<<(int)(((long long)N * C + 255) / 256), 256, 0, st>>>(workspace, d_d, N, C, bands);
+        GT_CUDA_LAUNCH_CHECK("gt_demod_act_bwd2(reduce)");
+    }
     return GT_OK;
 }

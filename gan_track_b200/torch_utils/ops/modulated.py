@@ -6,8 +6,8 @@
 Each is ONE pass over the activation instead of one per torch op; each backward is ONE pass that also produces every
 reduction (style / demodulation-coefficient / noise / bias gradients) in a fixed order.  Both first-order backward
 functions are themselves differentiable (the path-length regulariser differentiates the generator's backward,
-S3/training/loss.py:85-100); the second-order formulas are written with plain torch ops since they only run in the lazy
-Greg phase.
+S3/training/loss.py:85-100): their backward is again ONE fused pass (gt_mod_scale_bwd2 / gt_demod_act_bwd2) when no
+higher-order graph is being recorded, and the same formulas written with tensor ops otherwise.
 
 `applicable(x)` says whether a tensor can take the fused route (CUDA, fp16/fp32, dense channels-last, channel count the
 kernels support); callers keep the reference's op-by-op sequence otherwise.
@@ -90,6 +90,23 @@ class _ModScaleGrad(torch.autograd.Function):
         # gx = gy * s,  gs = sum_hw gy * x   =>   second-order terms below
         gy, x, s = ctx.saved_tensors
         d_gy = d_x = d_s = None
+        if not torch.is_grad_enabled() and applicable(gy) and applicable(x) and (ggx is not None or ggs is not None):
+            # one fused pass (csrc/modulated.cu: mod_scale_bwd2_kernel); the tensor-op formulas below are the differentiable form
+            n, c, h, w = x.shape
+            ggx_c = _cl(ggx) if ggx is not None else None
+            ggs_c = ggs.to(torch.float32).contiguous() if ggs is not None else None
+            if ctx.needs_input_grad[0]:
+                d_gy = torch.empty_like(x)
+            if ctx.needs_input_grad[1] and ggs is not None:
+                d_x = torch.empty_like(x)
+            if ctx.needs_input_grad[2] and ggx is not None:
+                d_s = torch.empty([n, c], dtype=torch.float32, device=x.device)
+            ws, nws = _ws(x)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().gt_mod_scale_bwd2(_lib.ptr(ggx_c), _lib.ptr(ggs_c), _lib.ptr(gy), _lib.ptr(x), _lib.ptr(s), _lib.ptr(d_gy), _lib.ptr(d_x),
+                                                         _lib.ptr(d_s), _lib.ptr(ws), nws, _lib.dtype_code(x), n, h * w, c, _lib.stream_of(x)), 'gt_mod_scale_bwd2')
+            _lib.count_launch(2 if d_s is not None else 1)
+            return d_gy, d_x, d_s
         if ctx.needs_input_grad[0]:
             d_gy = 0
             if ggx is not None:
@@ -175,6 +192,26 @@ class _DemodActGrad(torch.autograd.Function):
         #   gx = g1 * d,  gd = sum_hw g1 * x,  gnz = sum_c g1,  s0 = sum_hw g1
         gy, y, x, d = ctx.saved_tensors
         act, alpha, gain, clamp = ctx.cfg
+        if not torch.is_grad_enabled() and applicable(gy) and applicable(y) and any(t is not None for t in (ggx, ggd, ggnz, ggs0)):
+            # one fused pass (csrc/modulated.cu: demod_act_bwd2_kernel); the tensor-op formulas below are the differentiable form
+            n, c, h, w = y.shape
+            ggx_c = _cl(ggx) if ggx is not None else None
+            ggd_c = ggd.to(torch.float32).contiguous() if (ggd is not None and d is not None) else None
+            ggs0_c = ggs0.to(torch.float32).contiguous() if ggs0 is not None else None
+            ggnz_c = ggnz.to(y.dtype).expand(n, 1, h, w).contiguous() if ggnz is not None else None
+            d_gy = torch.empty_like(y) if ctx.needs_input_grad[0] else None
+            d_x = torch.empty_like(y) if (d is not None and ctx.needs_input_grad[2] and ggd_c is not None) else None
+            d_d = torch.empty([n, c], dtype=torch.float32, device=y.device) if (d is not None and ctx.needs_input_grad[3] and ggx is not None) else None
+            if d_gy is None and d_x is None and d_d is None:
+                return None, None, None, None, None, None, None, None, None
+            ws, nws = _ws(y)
+            with torch.cuda.device(y.device):
+                _lib.check(_lib.load().gt_demod_act_bwd2(_lib.ptr(ggx_c), _lib.ptr(ggd_c), _lib.ptr(ggnz_c), _lib.ptr(ggs0_c), _lib.ptr(gy), _lib.ptr(y),
+                                                         _lib.ptr(x if d is not None else None), _lib.ptr(d), _lib.ptr(d_gy), _lib.ptr(d_x), _lib.ptr(d_d),
+                                                         _lib.ptr(ws), nws, _lib.dtype_code(y), _ACT[act], alpha, gain, clamp, n, h * w, c,
+                                                         _lib.stream_of(y)), 'gt_demod_act_bwd2')
+            _lib.count_launch(2 if d_d is not None else 1)
+            return d_gy, None, d_x, d_d, None, None, None, None, None
         m = _slope(y, act, alpha, gain, clamp)
         d_gy = d_x = d_d = None
         if ctx.needs_input_grad[0]:

@@ -147,6 +147,18 @@ int gt_demod_act_fwd(const void* x, const float* d, const void* noise, const voi
 int gt_demod_act_bwd(const void* gy, const void* yref, const void* x, const float* d, void* gx, void* gnoise, float* gd,
                      float* s0, float* workspace, long long workspace_floats, int dtype, int act, float alpha, float gain,
                      float clamp, int N, long long P, int C, void* stream);
+/* Second-order passes (derivatives of gt_mod_scale_bwd / gt_demod_act_bwd with respect to their inputs; the path-length
+ * regulariser differentiates the generator's backward, S3/training/loss.py:85-100).  Cotangents that are absent and
+ * outputs that are not wanted are NULL.
+ *   gt_mod_scale_bwd2:  d_gy = ggx * s + ggs * x;  d_x = ggs * gy;  d_s[n,c] = sum_p ggx * gy
+ *   gt_demod_act_bwd2:  m = gain * act'(yref) * [|yref| < clamp], g1 = gy * m;
+ *                       d_gy = m * (ggx * d + ggd * x + ggnz + ggs0);  d_x = ggd * g1;  d_d[n,c] = sum_p ggx * g1 */
+int gt_mod_scale_bwd2(const void* ggx, const float* ggs, const void* gy, const void* x, const float* s, void* d_gy, void* d_x,
+                      float* d_s, float* workspace, long long workspace_floats, int dtype, int N, long long P, int C, void* stream);
+int gt_demod_act_bwd2(const void* ggx, const float* ggd, const void* ggnz, const float* ggs0, const void* gy, const void* yref,
+                      const void* x, const float* d, void* d_gy, void* d_x, float* d_d, float* workspace,
+                      long long workspace_floats, int dtype, int act, float alpha, float gain, float clamp, int N, long long P,
+                      int C, void* stream);
 
 #ifdef __cplusplus
 }
