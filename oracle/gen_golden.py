@@ -27,9 +27,16 @@ def import_reference():
         sys.modules.setdefault(m, types.ModuleType(m))
     orig = torch._C._jit_get_operation
     if not getattr(orig, '_gt_shim', False):
+        class _CallableTuple(tuple):
+            """(op, overload_names) as torch 2.x returns it -- torch's own callers unpack it -- that can also be CALLED like the
+            bare op torch 1.x returned, which is what the reference does (OPS/grid_sample_gradfix.py:60-65)."""
+
+            def __call__(self, *a, **k):
+                return self[0](*a, **k)
+
         def shim(name):
             r = orig(name)
-            return r[0] if isinstance(r, tuple) else r
+            return _CallableTuple(r) if isinstance(r, tuple) else r
         shim._gt_shim = True
         torch._C._jit_get_operation = shim
     import warnings
