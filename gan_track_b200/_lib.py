@@ -36,6 +36,9 @@ _PROTOTYPES = {
     'gt_demod_act_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _i, _ll, _i, _vp]),
     'gt_mod_scale_bwd2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _i, _vp]),
     'gt_demod_act_bwd2': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _i, _ll, _i, _vp]),
+    'gt_fc_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    'gt_fc_dgrad': (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    'gt_fc_wgrad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     'gt_conv_igemm_config': (_i, [_i]),
     'gt_conv_wgrad_config': (_i, [_i]),
     'gt_conv_pack_weight_f16': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),

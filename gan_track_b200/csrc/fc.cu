@@ -1,0 +1,217 @@
+// fc.cu -- the fully-connected layers of the path (mapping networks, style affines, discriminator epilogue) at training
+// batch sizes: fp32, M = batch <= 64 rows.
+//
+// Reference: FullyConnectedLayer.forward (S3/training/networks_stylegan2.py:115-126; S3 = /root/reference/src/models/stylegan3)
+//     w = weight * weight_gain;  b = bias * bias_gain;  y = addmm(b, x, w.t())        (+ bias_act for non-linear layers)
+// i.e. per layer and pass two scaling kernels, a library GEMM whose tiles are sized for M >= 128 (the 512x512 layers run
+// 11 us, the 8192 -> 512 discriminator layer 110-180 us per GEMM in the step profile, profiles/r01b_step_profile.txt) and
+// often a split-K reduction.  With M <= 64 the problem is a stream over the weight matrix; the three kernels below read
+// (or write) it exactly once, coalesced, and fold the gains in:
+//     gt_fc_fwd     y[m,o]  = wgain * sum_i x[m,i]  w[o,i] + bgain * b[o]
+//     gt_fc_dgrad   dx[m,i] = wgain * sum_o dy[m,o] w[o,i]
+//     gt_fc_wgrad   dw[o,i] = wgain * sum_m dy[m,o] x[m,i];   db[o] = bgain * sum_m dy[m,o]
+// The family is closed under differentiation (the derivative of each is another of the three), which is what the
+// path-length and R1 double backwards need.  All reductions have a fixed order.
+#include "gt_common.cuh"
+
+namespace {
+
+constexpr int FC_KC = 128;     // k-chunk of the forward kernel (one float4 per lane)
+
+// sum over the 32 lanes of MB per-lane values; afterwards acc[0] on lane l is the total of value l (+32 for the upper half)
+template <int N>
+__device__ __forceinline__ void warp_transpose_sum(float (&acc)[N], int lane) {
+#pragma unroll
+    for (int off = N / 2; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int j = 0; j < off; j++) {
+            const bool up = (lane & off) != 0;
+            const float send = up ? acc[j] : acc[j + off];
+            const float keep = up ? acc[j + off] : acc[j];
+            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// one warp per output feature, 8 features per CTA; x staged per 128-wide k-chunk
+template <int MB>
+__global__ void __launch_bounds__(256) fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                     float* __restrict__ y, int M, int I, int O, float wgain, float bgain) {
+    __shared__ float4 xs[MB][FC_KC / 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp;
+    float acc[MB];
+#pragma unroll
+    for (int m = 0; m < MB; m++) acc[m] = 0.f;
+    for (int k0 = 0; k0 < I; k0 += FC_KC) {
+        // the weight vector of this chunk is requested first so that its latency overlaps the staging of x
+        const int k = k0 + lane * 4;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O && k < I) wv = *reinterpret_cast<const float4*>(w + (long long)o * I + k);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < MB * (FC_KC / 4); idx += 256) {
+            const int m = idx / (FC_KC / 4), q = idx - m * (FC_KC / 4);
+            const int kk = k0 + q * 4;
+            xs[m][q] = (m < M && kk < I) ? *reinterpret_cast<const float4*>(x + (long long)m * I + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+            const float4 xv = xs[m][lane];
+            acc[m] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+        }
+    }
+    if (MB >= 32) {
+        float lo[32];
+#pragma unroll
+        for (int m = 0; m < 32; m++) lo[m] = acc[m];
+        warp_transpose_sum<32>(lo, lane);
+        if (o < O && lane < M) y[(long long)lane * O + o] = lo[0] * wgain + (b ? b[o] * bgain : 0.f);
+        if (MB == 64) {
+            float hi[32];
+#pragma unroll
+            for (int m = 0; m < 32; m++) hi[m] = acc[(MB == 64 ? 32 : 0) + m];
+            warp_transpose_sum<32>(hi, lane);
+            if (o < O && lane + 32 < M) y[(long long)(lane + 32) * O + o] = hi[0] * wgain + (b ? b[o] * bgain : 0.f);
+        }
+    } else {
+        // MB in {8, 16}: replicate to 32 slots would waste shuffles; plain butterfly per value
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+            const float s = warp_sum(acc[m]);
+            if (o < O && lane == 0 && m < M) y[(long long)m * O + o] = s * wgain + (b ? b[o] * bgain : 0.f);
+        }
+    }
+}
+
+// lanes walk 32 input features (coalesced rows of w), the 8 warps split the output features, fixed-order combine
+template <int MB>
+__global__ void __launch_bounds__(256) fc_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int M, int I,
+                                                       int O, float wgain) {
+    constexpr int OC = 128;                      // output features staged per round (16 weight loads in flight per thread)
+    __shared__ float dys[OC][MB];
+    __shared__ float red[8][8][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 32 + lane;
+    float acc[MB];
+#pragma unroll
+    for (int m = 0; m < MB; m++) acc[m] = 0.f;
+    for (int o0 = 0; o0 < O; o0 += OC) {
+        // this warp's 8 weight rows of the round are requested together (8 loads in flight) before the dy staging barrier
+        float wv[OC / 8];
+#pragma unroll
+        for (int j = 0; j < OC / 8; j++) {
+            const int o = o0 + warp + 8 * j;
+            wv[j] = (o < O && i < I) ? __ldg(w + (long long)o * I + i) : 0.f;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < OC * MB; idx += 256) {
+            const int m = idx / OC, oo = idx - m * OC;         // consecutive threads -> consecutive o: coalesced reads of dy[m, :]
+            dys[oo][m] = (m < M && o0 + oo < O) ? dy[(long long)m * O + o0 + oo] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < OC / 8; j++) {
+            const int oo = warp + 8 * j;
+#pragma unroll
+            for (int m = 0; m < MB; m++) acc[m] += dys[oo][m] * wv[j];
+        }
+    }
+    // combine the 8 warps in warp order, 8 rows at a time (keeps the scratch at 8.4 KB for any MB)
+#pragma unroll
+    for (int mb = 0; mb < MB; mb += 8) {
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < 8; mm++) red[warp][mm][lane] = acc[mb + mm];
+        __syncthreads();
+        {
+            const int mm = threadIdx.x >> 5, l = threadIdx.x & 31;       // 256 threads = 8 rows x 32 columns
+            const int m = mb + mm, ii = blockIdx.x * 32 + l;
+            if (m < M && ii < I) {
+                float s = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < 8; wv++) s += red[wv][mm][l];
+                dx[(long long)m * I + ii] = s * wgain;
+            }
+        }
+    }
+}
+
+// a thread owns one input feature (x column in registers), a CTA 16 output features
+template <int MB>
+__global__ void __launch_bounds__(256) fc_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                                       float* __restrict__ db, int M, int I, int O, float wgain, float bgain) {
+    constexpr int OB = 16;
+    __shared__ float dys[OB][MB];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int o0 = blockIdx.y * OB;
+    for (int idx = threadIdx.x; idx < OB * MB; idx += 256) {
+        const int m = idx / OB, oo = idx - m * OB;
+        dys[oo][m] = (m < M && o0 + oo < O) ? dy[(long long)m * O + o0 + oo] : 0.f;
+    }
+    float xr[MB];
+#pragma unroll
+    for (int m = 0; m < MB; m++) xr[m] = (m < M && i < I) ? x[(long long)m * I + i] : 0.f;
+    __syncthreads();
+    if (i < I) {
+#pragma unroll 4
+        for (int oo = 0; oo < OB; oo++) {
+            if (o0 + oo < O) {
+                float s = 0.f;
+#pragma unroll
+                for (int m = 0; m < MB; m++) s += dys[oo][m] * xr[m];
+                dw[(long long)(o0 + oo) * I + i] = s * wgain;
+            }
+        }
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x < OB && o0 + threadIdx.x < O) {
+        float s = 0.f;
+        for (int m = 0; m < MB; m++) s += dys[threadIdx.x][m];
+        db[o0 + threadIdx.x] = s * bgain;
+    }
+}
+
+inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace
+
+#define GT_FC_MB(M_, CALL)                 \
+    if (M_ <= 8) { CALL(8) }               \
+    else if (M_ <= 16) { CALL(16) }        \
+    else if (M_ <= 32) { CALL(32) }        \
+    else { CALL(64) }
+
+extern "C" int gt_fc_fwd(const float* x, const float* w, const float* b, float* y, int M, int I, int O, float wgain, float bgain, void* stream) {
+    GT_REQUIRE(x && w && y, "gt_fc_fwd: null pointer");
+    GT_REQUIRE(M >= 1 && M <= 64 && I >= 1 && O >= 1, "gt_fc_fwd: shape M=%d I=%d O=%d not supported (1 <= M <= 64)", M, I, O);
+    GT_REQUIRE(I % 4 == 0 && al16(x) && al16(w), "gt_fc_fwd: in_features must be a multiple of 4 and x, w 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(MB_) fc_fwd_kernel<MB_><<<(O + 7) / 8, 256, 0, st>>>(x, w, b, y, M, I, O, wgain, bgain);
+    GT_FC_MB(M, CALL)
+#undef CALL
+    GT_CUDA_LAUNCH_CHECK("gt_fc_fwd");
+    return GT_OK;
+}
+
+extern "C" int gt_fc_dgrad(const float* dy, const float* w, float* dx, int M, int I, int O, float wgain, void* stream) {
+    GT_REQUIRE(dy && w && dx, "gt_fc_dgrad: null pointer");
+    GT_REQUIRE(M >= 1 && M <= 64 && I >= 1 && O >= 1, "gt_fc_dgrad: shape M=%d I=%d O=%d not supported (1 <= M <= 64)", M, I, O);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(MB_) fc_dgrad_kernel<MB_><<<(I + 31) / 32, 256, 0, st>>>(dy, w, dx, M, I, O, wgain);
+    GT_FC_MB(M, CALL)
+#undef CALL
+    GT_CUDA_LAUNCH_CHECK("gt_fc_dgrad");
+    return GT_OK;
+}
+
+extern "C" int gt_fc_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int I, int O, float wgain, float bgain, void* stream) {
+    GT_REQUIRE(dy && x && dw, "gt_fc_wgrad: null pointer");
+    GT_REQUIRE(M >= 1 && M <= 64 && I >= 1 && O >= 1, "gt_fc_wgrad: shape M=%d I=%d O=%d not supported (1 <= M <= 64)", M, I, O);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((I + 255) / 256, (O + 15) / 16);
+#define CALL(MB_) fc_wgrad_kernel<MB_><<<grid, 256, 0, st>>>(dy, x, dw, db, M, I, O, wgain, bgain);
+    GT_FC_MB(M, CALL)
+#undef CALL
+    GT_CUDA_LAUNCH_CHECK("gt_fc_wgrad");
+    return GT_OK;
+}

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..torch_utils import misc
-from ..torch_utils.ops import bias_act, conv2d_resample, fma, modulated, upfirdn2d
+from ..torch_utils.ops import bias_act, conv2d_resample, fc, fma, modulated, upfirdn2d
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -103,6 +103,12 @@ class FullyConnectedLayer(torch.nn.Module):
         self.bias_gain = lr_multiplier
 
     def forward(self, x):
+        if fc.applicable(x, self.weight):
+            # one kernel for gains + GEMM + bias (csrc/fc.cu); the activation of non-linear layers stays with bias_act
+            y = fc.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain)
+            if self.activation == 'linear':
+                return y
+            return bias_act.bias_act(y, None, act=self.activation)
         w = self.weight.to(x.dtype) * self.weight_gain
         b = self.bias
         if b is not None:

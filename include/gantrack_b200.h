@@ -112,6 +112,17 @@ int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long
                         int pad, void* dw, long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace,
                         long long workspace_floats, void* stream);
 
+/* ---- fully-connected layers at training batch sizes (fp32, 1 <= M <= 64 rows) ----------------------------------------
+ * Replace `w = weight * weight_gain; b = bias * bias_gain; addmm(b, x, w.t())` of FullyConnectedLayer.forward
+ * (S3/training/networks_stylegan2.py:115-126) and its autograd.  x: [M,I], w: [O,I], b: [O] or NULL, y / dy: [M,O], all
+ * contiguous fp32; I a multiple of 4 and x, w 16-byte aligned for gt_fc_fwd.
+ *   gt_fc_fwd:    y  = wgain * x . w^T + bgain * b
+ *   gt_fc_dgrad:  dx = wgain * dy . w
+ *   gt_fc_wgrad:  dw = wgain * dy^T . x;  db = bgain * sum_m dy   (db may be NULL) */
+int gt_fc_fwd(const float* x, const float* w, const float* b, float* y, int M, int I, int O, float wgain, float bgain, void* stream);
+int gt_fc_dgrad(const float* dy, const float* w, float* dx, int M, int I, int O, float wgain, void* stream);
+int gt_fc_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int I, int O, float wgain, float bgain, void* stream);
+
 /* ---- ADA geometric warp (fp32) ------------------------------------------------------------------------------------
  * Replaces the op sequence of S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps,
  * up=2) -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE

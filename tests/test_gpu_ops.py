@@ -328,3 +328,40 @@ def test_fma_and_grid_sample(golden):
     g1, = torch.autograd.grad(out.square().sum(), img, create_graph=True)
     g2, = torch.autograd.grad(g1.square().sum(), img)          # double backward must exist (R1 through the ADA pipe)
     assert torch.isfinite(g2).all()
+
+
+# ---------------------------------------------------------------------------------------------------- fully-connected
+
+@pytest.mark.parametrize('M,I,O,bias', [(32, 512, 512, True), (32, 8192, 512, True), (16, 512, 64, True), (4, 32, 32, False), (64, 516, 130, True),
+                                        (7, 512, 1, True), (33, 64, 512, False)])
+def test_fc_linear_matches_addmm_to_second_order(M, I, O, bias):
+    """csrc/fc.cu against the reference's op sequence (S3/training/networks_stylegan2.py:115-126): value, first-order gradients of
+    x / weight / bias, and the second-order terms the R1 and path-length passes need (gradient of <dx, v> w.r.t. dy-side inputs)."""
+    from gan_track_b200.torch_utils.ops import fc
+    torch.manual_seed(M * 7 + O)
+    wg, bg = 1.0 / np.sqrt(I), 0.7
+    x0 = torch.randn(M, I, device=DEV)
+    w0 = torch.randn(O, I, device=DEV)
+    b0 = torch.randn(O, device=DEV) if bias else None
+    dy = torch.randn(M, O, device=DEV)
+    v = torch.randn(M, I, device=DEV)
+    outs = []
+    for ours in (True, False):
+        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if bias else None
+        assert fc.applicable(x, w)
+        if ours:
+            y = fc.linear(x, w, b, wg, bg)
+        else:
+            y = x.matmul((w * wg).t())
+            if bias:
+                y = y + (b * bg).unsqueeze(0)
+        ins = [x, w] + ([b] if bias else [])
+        g = torch.autograd.grad(y, ins, dy, create_graph=True)
+        q = (g[0] * v).sum() + (g[1] * g[1]).sum() * 0.1
+        g2 = torch.autograd.grad(q, [x, w], allow_unused=True)
+        outs.append([y.detach()] + [t_.detach() for t_ in g] + [t_.detach() for t_ in g2 if t_ is not None])
+    assert len(outs[0]) == len(outs[1])
+    for a, c in zip(outs[0], outs[1]):
+        assert a.shape == c.shape
+        assert_close(a, c.cpu(), 2e-5, 'fc')
