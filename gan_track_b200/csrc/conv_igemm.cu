@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kchunks = p.Cin / BK;
+    const int kel = p.tf32 ? 32 : BK;           // channels per 128-byte k-chunk
+    const int kchunks = p.Cin / kel;
     const int nkb = ph.ntaps * kchunks;
 
     if (warp == 0) {
@@ -112,8 +113,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
                 for (int kc = 0; kc < kchunks; kc++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
-                    tma_load_4d(sA + stage * L::A_BYTES, &tmA, &full[stage], kc * BK, cx, cy, n0);
-                    tma_load_3d(sB + stage * L::B_BYTES, &tmB, &full[stage], kc * BK, nt * BN, slab);
+                    tma_load_4d(sA + stage * L::A_BYTES, &tmA, &full[stage], kc * kel, cx, cy, n0);
+                    tma_load_3d(sB + stage * L::B_BYTES, &tmB, &full[stage], kc * kel, nt * BN, slab);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -124,16 +125,20 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(BM, BN, 0, 0, 0);
+            constexpr uint32_t idesc = umma_idesc(BM, BN, 0, 0, 0), idesc_tf32 = umma_idesc(BM, BN, 2, 0, 0);
+            const bool tf32 = p.tf32 != 0;
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA + stage * L::A_BYTES), b0 = smem_u32(sB + stage * L::B_BYTES);
+                // one MMA consumes 32 bytes of every row: K = 16 fp16 or K = 8 tf32 elements -- same byte geometry for both
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++)
-                    umma_f16(tmem_base, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kb | k) != 0));
+                for (int k = 0; k < 4; k++) {
+                    if (tf32) umma_tf32(tmem_base, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc_tf32, (uint32_t)((kb | k) != 0));
+                    else umma_f16(tmem_base, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kb | k) != 0));
+                }
                 umma_commit(&empty[stage]);   // stage reusable once these MMAs have read it
                 if (++stage == STAGES) {
                     stage = 0;
@@ -152,8 +157,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
         const int ln = m >> (bw_log2 + bh_log2);
         const int a = oy0 + lh, b = ox0 + lw, n = n0 + ln;
         const bool valid = (a < ph.OHp) && (b < ph.OWp) && (n < p.N);
-        __half* yp = p.y + (long long)n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
-                     (long long)(b * p.out_stride + ph.off_x) * p.ys_w + nt * BN;
+        const long long yoff = (long long)n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
+                               (long long)(b * p.out_stride + ph.off_x) * p.ys_w + nt * BN;
         mbar_wait(tfull, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -161,21 +166,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
             tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    uint4 o;
-                    __half2 h0 = __floats2half2_rn(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-                    __half2 h1 = __floats2half2_rn(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-                    __half2 h2 = __floats2half2_rn(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-                    __half2 h3 = __floats2half2_rn(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
-                    o.x = *reinterpret_cast<uint32_t*>(&h0);
-                    o.y = *reinterpret_cast<uint32_t*>(&h1);
-                    o.z = *reinterpret_cast<uint32_t*>(&h2);
-                    o.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(yp + c * 32 + v * 8) = o;
-                }
-            }
+            if (valid) conv_store32(p.y, yoff + c * 32, p.tf32, r);
         }
     }
     tc_fence_before();
@@ -258,17 +249,18 @@ extern "C" int gt_conv_pack_weight_f16(const void* w, long long s_co, long long 
     return GT_OK;
 }
 
-extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
-                                   long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
-                                   int pad, int transposed, void* stream) {
+static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                             long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
+                             int pad, int transposed, int tf32, void* stream) {
+    const int esz = tf32 ? 4 : 2, kel = tf32 ? 32 : BK, al = 16 / esz;
     GT_REQUIRE(x && wpacked && y, "gt_conv2d_igemm_f16: null pointer");
     GT_REQUIRE(N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "gt_conv2d_igemm_f16: empty tensor");
-    GT_REQUIRE(Cin % BK == 0 && Cout % 64 == 0, "gt_conv2d_igemm_f16: Cin (%d) and Cout (%d) must be multiples of 64", Cin, Cout);
+    GT_REQUIRE(Cin % kel == 0 && Cout % 64 == 0, "gt_conv2d_igemm: Cin (%d) must be a multiple of %d and Cout (%d) of 64", Cin, kel, Cout);
     GT_REQUIRE(KH * KW <= MAX_TAPS && KH >= 1 && KW >= 1, "gt_conv2d_igemm_f16: kernel %dx%d not supported", KH, KW);
     GT_REQUIRE(stride == 1 || stride == 2, "gt_conv2d_igemm_f16: stride %d not supported", stride);
     GT_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)y & 15) == 0, "gt_conv2d_igemm_f16: pointers must be 16-byte aligned");
-    GT_REQUIRE(xs_w % 8 == 0 && xs_h % 8 == 0 && xs_n % 8 == 0 && ys_w % 8 == 0 && ys_h % 8 == 0 && ys_n % 8 == 0,
-               "gt_conv2d_igemm_f16: strides must be multiples of 8 elements");
+    GT_REQUIRE(xs_w % al == 0 && xs_h % al == 0 && xs_n % al == 0 && ys_w % al == 0 && ys_h % al == 0 && ys_n % al == 0,
+               "gt_conv2d_igemm: strides must be multiples of 16 bytes");
     GT_REQUIRE(pad >= 0 && pad < 8, "gt_conv2d_igemm_f16: pad %d not supported", pad);
 
     ConvParams p;
@@ -276,7 +268,8 @@ extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h
     p.N = N;
     p.Cin = Cin;
     p.Cout = Cout;
-    p.y = (__half*)y;
+    p.y = y;
+    p.tf32 = tf32;
     p.ys_n = ys_n;
     p.ys_h = ys_h;
     p.ys_w = ys_w;
@@ -361,22 +354,23 @@ extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h
     const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
     p.n_tiles = Cout / BN;
 
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)xs_w * 2, (cuuint64_t)xs_h * 2, (cuuint64_t)xs_n * 2};
-        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * p.in_stride), (cuuint32_t)(bh * p.in_stride), (cuuint32_t)bn};
+        cuuint64_t strides[3] = {(cuuint64_t)xs_w * esz, (cuuint64_t)xs_h * esz, (cuuint64_t)xs_n * esz};
+        cuuint32_t box[4] = {(cuuint32_t)kel, (cuuint32_t)(bw * p.in_stride), (cuuint32_t)(bh * p.in_stride), (cuuint32_t)bn};
         cuuint32_t estr[4] = {1, (cuuint32_t)p.in_stride, (cuuint32_t)p.in_stride, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = encode(&tmA, dt, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         GT_REQUIRE(r == CUDA_SUCCESS, "gt_conv2d_igemm_f16: activation tensor map rejected (CUresult %d)", (int)r);
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(KH * KW)};
-        cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
-        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)Cin * Cout * esz};
+        cuuint32_t box[3] = {(cuuint32_t)kel, (cuuint32_t)BN, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(wpacked), dims, strides, box, estr,
+        CUresult r = encode(&tmB, dt, 3, const_cast<void*>(wpacked), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         GT_REQUIRE(r == CUDA_SUCCESS, "gt_conv2d_igemm_f16: weight tensor map rejected (CUresult %d)", (int)r);
@@ -385,4 +379,96 @@ extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h
     if (BN == 256) return launch_conv<256, 4>(tmA, tmB, p, st);
     if (BN == 128) return launch_conv<128, 3>(tmA, tmB, p, st);
     return launch_conv<64, 4>(tmA, tmB, p, st);
+}
+
+extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                                   long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
+                                   int pad, int transposed, void* stream) {
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, stream);
+}
+
+// ---- fp32 convolutions on the tensor cores: 3 x TF32 ------------------------------------------------------------------
+// The fp32 blocks (4x4 .. 16x16, 512 channels) must stay fp32-accurate (north star 1e-5; the reference turns TF32 off,
+// S3/training/training_loop_mi_multimodal.py:169-170).  A TF32 operand keeps 11 significant bits, so each fp32 value is
+// split into big = rna_tf32(v) and small = rna_tf32(v - big) (22 bits together) and the product is taken as
+//     x w  ~=  x_big w_big + x_big w_small + x_small w_big          (dropped: x_small w_small, ~2^-22 relative)
+// with fp32 accumulation in TMEM.  The three terms are ONE TF32 convolution over a 3x wider channel dimension:
+//     activations [N,H,W,3C] = [x_big | x_big | x_small],  weights [tap][Cout][3C] = [w_big | w_small | w_big]
+// which is what gt_split_tf32x3 / gt_conv_pack_weight_tf32x3 produce and gt_conv2d_igemm_tf32 (the same kernels as the fp16
+// path, kind::tf32, 32 channels per 128-byte chunk, fp32 output) consumes.
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// x: [N,C,H,W] with arbitrary element strides  ->  out: [N,H,W,3C] contiguous
+__global__ void __launch_bounds__(256) split_tf32x3_kernel(const float* __restrict__ x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C,
+                                                           int H, int W, float* __restrict__ out) {
+    const long long total = (long long)N * H * W * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int w = (int)(r % W);
+        r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        const float v = x[n * s_n + c * s_c + h * s_h + w * s_w];
+        const float big = rna_tf32(v);
+        const float small = rna_tf32(v - big);
+        float* o = out + (i / C) * (3ll * C) + c;
+        o[0] = big;
+        o[C] = big;
+        o[2 * C] = small;
+    }
+}
+
+// out[t][co][0:C | C:2C | 2C:3C] = big | small | big of w[co * s_co + ci * s_ci + r * s_r + s * s_s]
+__global__ void __launch_bounds__(256) pack_weight_tf32x3_kernel(const float* __restrict__ w, long long s_co, long long s_ci, long long s_r, long long s_s,
+                                                                 int Cout, int Cin, int KH, int KW, float* __restrict__ out) {
+    const long long total = (long long)KH * KW * Cout * Cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        long long r_ = i / Cin;
+        const int co = (int)(r_ % Cout);
+        const int t = (int)(r_ / Cout);
+        const int r = t / KW, s = t - r * KW;
+        const float v = w[co * s_co + ci * s_ci + r * s_r + s * s_s];
+        const float big = rna_tf32(v);
+        const float small = rna_tf32(v - big);
+        float* o = out + ((long long)t * Cout + co) * (3ll * Cin) + ci;
+        o[0] = big;
+        o[Cin] = small;
+        o[2 * Cin] = big;
+    }
+}
+
+extern "C" int gt_split_tf32x3(const void* x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C, int H, int W, void* out,
+                               void* stream) {
+    GT_REQUIRE(x && out, "gt_split_tf32x3: null pointer");
+    GT_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "gt_split_tf32x3: bad shape");
+    const long long total = (long long)N * H * W * C;
+    long long g = (total + 255) / 256;
+    if (g > (long long)gt_num_sms() * 16) g = (long long)gt_num_sms() * 16;
+    split_tf32x3_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)x, s_n, s_c, s_h, s_w, N, C, H, W, (float*)out);
+    GT_CUDA_LAUNCH_CHECK("gt_split_tf32x3");
+    return GT_OK;
+}
+
+extern "C" int gt_conv_pack_weight_tf32x3(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin, int KH, int KW,
+                                          void* out, void* stream) {
+    GT_REQUIRE(w && out, "gt_conv_pack_weight_tf32x3: null pointer");
+    GT_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "gt_conv_pack_weight_tf32x3: bad shape");
+    const long long total = (long long)KH * KW * Cout * Cin;
+    long long g = (total + 255) / 256;
+    if (g > (long long)gt_num_sms() * 16) g = (long long)gt_num_sms() * 16;
+    pack_weight_tf32x3_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)w, s_co, s_ci, s_r, s_s, Cout, Cin, KH, KW, (float*)out);
+    GT_CUDA_LAUNCH_CHECK("gt_conv_pack_weight_tf32x3");
+    return GT_OK;
+}
+
+extern "C" int gt_conv2d_igemm_tf32(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                                    long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
+                                    int pad, int transposed, void* stream) {
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 1, stream);
 }

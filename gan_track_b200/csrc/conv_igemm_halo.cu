@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kchunks = p.Cin / 64;
+    const int kel = p.tf32 ? 32 : 64;           // channels per 128-byte chunk
+    const int kchunks = p.Cin / kel;
     const uint32_t a_bytes = (uint32_t)(p.halo_w * p.halo_h) * 128u;
     const uint32_t row_pitch = (uint32_t)p.halo_w * 128u;
 
@@ -119,13 +120,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
                     const uint32_t ab = a_it & 1;
                     mbar_wait(&a_empty[ab], ((a_it >> 1) & 1) ^ 1);
                     mbar_arrive_expect_tx(&a_full[ab], a_bytes);
-                    tma_load_4d(sA + ab * L::A_BYTES, &tmA, &a_full[ab], kc * 64, cx, cy, it.n);
+                    tma_load_4d(sA + ab * L::A_BYTES, &tmA, &a_full[ab], kc * kel, cx, cy, it.n);
                     a_it++;
                     for (int t = 0; t < ph.ntaps; t++) {
                         const uint32_t bs = b_it % SB;
                         mbar_wait(&b_empty[bs], ((b_it / SB) & 1) ^ 1);
                         mbar_arrive_expect_tx(&b_full[bs], L::B_BYTES);
-                        tma_load_3d(sB + bs * L::B_BYTES, &tmB, &b_full[bs], kc * 64, it.nt * BN, ph.tw[t]);
+                        tma_load_3d(sB + bs * L::B_BYTES, &tmB, &b_full[bs], kc * kel, it.nt * BN, ph.tw[t]);
                         b_it++;
                     }
                 }
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0, 0);
+            constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0, 0), idesc_tf32 = umma_idesc(128, BN, 2, 0, 0);
+            const bool tf32 = p.tf32 != 0;
             uint32_t a_it = 0, b_it = 0, t_it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const Item it = decode_item(p, item, TILE_W);
@@ -159,9 +161,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
 #pragma unroll
                         for (int j = 0; j < MT; j++) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                umma_f16(acc + j * BN, umma_smem_desc(at + j * (SUB_W * 128) + k * 32, 0, row_pitch), umma_smem_desc(b0 + k * 32, 0, 1024),
-                                         idesc, (uint32_t)((kc | t | k) != 0));
+                            for (int k = 0; k < 4; k++) {      // 32 bytes of every row per MMA: K = 16 fp16 or K = 8 tf32
+                                if (tf32)
+                                    umma_tf32(acc + j * BN, umma_smem_desc(at + j * (SUB_W * 128) + k * 32, 0, row_pitch),
+                                              umma_smem_desc(b0 + k * 32, 0, 1024), idesc_tf32, (uint32_t)((kc | t | k) != 0));
+                                else
+                                    umma_f16(acc + j * BN, umma_smem_desc(at + j * (SUB_W * 128) + k * 32, 0, row_pitch),
+                                             umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kc | t | k) != 0));
+                            }
                         }
                         umma_commit(&b_empty[bs]);
                         b_it++;
@@ -191,28 +198,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
             for (int j = 0; j < MT; j++) {
                 const int b = it.ox0 + j * SUB_W + lw;
                 const bool valid = (a < ph.OHp) && (b < ph.OWp);
-                __half* yp = p.y + (long long)it.n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
-                             (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN;
+                const long long yoff = (long long)it.n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
+                                       (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN;
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; c++) {
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c * 32), r);
                     tmem_ld_wait();
-                    if (valid) {
-#pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            uint4 o;
-                            __half2 h0 = __floats2half2_rn(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-                            __half2 h1 = __floats2half2_rn(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-                            __half2 h2 = __floats2half2_rn(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-                            __half2 h3 = __floats2half2_rn(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
-                            o.x = *reinterpret_cast<uint32_t*>(&h0);
-                            o.y = *reinterpret_cast<uint32_t*>(&h1);
-                            o.z = *reinterpret_cast<uint32_t*>(&h2);
-                            o.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(yp + c * 32 + v * 8) = o;
-                        }
-                    }
+                    if (valid) conv_store32(p.y, yoff + c * 32, p.tf32, r);
                 }
             }
             tc_fence_before();
@@ -308,22 +301,25 @@ int gt_launch_conv_halo(const void* x, long long xs_n, long long xs_h, long long
 
     gt_encode_tiled_fn encode = gt_get_encode_tiled();
     GT_REQUIRE(encode != nullptr, "gt_conv2d_igemm_f16: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t esz = p.tf32 ? 4 : 2;
+    const int kel = p.tf32 ? 32 : 64;
+    const CUtensorMapDataType dt = p.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.N};
-        cuuint64_t strides[3] = {(cuuint64_t)xs_w * 2, (cuuint64_t)xs_h * 2, (cuuint64_t)xs_n * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)p.halo_w, (cuuint32_t)p.halo_h, 1};
+        cuuint64_t strides[3] = {(cuuint64_t)xs_w * esz, (cuuint64_t)xs_h * esz, (cuuint64_t)xs_n * esz};
+        cuuint32_t box[4] = {(cuuint32_t)kel, (cuuint32_t)p.halo_w, (cuuint32_t)p.halo_h, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = encode(&tmA, dt, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         GT_REQUIRE(r == CUDA_SUCCESS, "gt_conv2d_igemm_f16 (halo): activation tensor map rejected (CUresult %d)", (int)r);
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)ntaps_total};
-        cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cin * p.Cout * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)p.Cin * esz, (cuuint64_t)p.Cin * p.Cout * esz};
+        cuuint32_t box[3] = {(cuuint32_t)kel, (cuuint32_t)BN, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(wpacked), dims, strides, box, estr,
+        CUresult r = encode(&tmB, dt, 3, const_cast<void*>(wpacked), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         GT_REQUIRE(r == CUDA_SUCCESS, "gt_conv2d_igemm_f16 (halo): weight tensor map rejected (CUresult %d)", (int)r);

@@ -60,7 +60,62 @@ def pack_weight(w, transpose):
     return packed
 
 
+# fp32 layers on the tensor cores as 3 x TF32.  OFF by default: measured on B200 (tools/test_tf32x3.py) the products are
+# fp32-accurate but the tensor core adds every K = 8 MMA into its fp32 accumulator with truncation, and that bias grows
+# linearly with the number of accumulator updates -- 7e-6 relative for the 64..128-channel 3x3 cases (<= 432 updates) but
+# 3e-5 .. 5e-5 for the 512-channel 3x3 layers of the fp32 blocks (1728 updates), above the 1e-5 the north star asks of fp32
+# layers (cuDNN's own fp32 kernels sit at 2e-5 there).  Needs two-level accumulation (TMEM partials promoted to fp32
+# registers every ~64 updates) before it can take over; until then those layers keep the library's true-fp32 route.
+tf32x3_enabled = False
+
+
+def covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
+    if not (enabled and tf32x3_enabled) or x.dtype != torch.float32 or w.dtype != torch.float32 or not x.is_cuda or groups != 1:
+        return False
+    if stride[0] != stride[1] or padding[0] != padding[1] or tuple(output_padding) != (0, 0) or stride[0] not in (1, 2):
+        return False
+    kh, kw = w.shape[2:]
+    cin, cout = (w.shape[0], w.shape[1]) if transpose else (w.shape[1], w.shape[0])
+    if x.shape[1] != cin or cin % 32 != 0 or cout % 64 != 0 or kh * kw > 9 or padding[0] >= 8:
+        return False
+    if transpose and stride[0] == 2 and padding[0] != 0:
+        return False
+    return min(x.shape) > 0
+
+
+def igemm_forward_tf32x3(x, w, *, transpose, output_padding, stride, padding, groups):
+    """fp32 convolution / transposed convolution as ONE TF32 implicit GEMM over [x_big | x_big | x_small] x
+    [w_big | w_small | w_big] (csrc/conv_igemm.cu).  Output: fp32, channels-last."""
+    lib = _lib.load()
+    N, cin, H, W = x.shape
+    kh, kw = w.shape[2:]
+    cout = w.shape[1] if transpose else w.shape[0]
+    OH, OW = out_size(H, W, kh, kw, stride[0], padding[0], transpose)
+    if OH <= 0 or OW <= 0:
+        return None
+    with torch.cuda.device(x.device):
+        st = _lib.stream_of(x)
+        xs = torch.empty([N, H, W, 3 * cin], dtype=torch.float32, device=x.device)
+        sx = x.stride()
+        _lib.check(lib.gt_split_tf32x3(_lib.ptr(x), sx[0], sx[1], sx[2], sx[3], N, cin, H, W, _lib.ptr(xs), st), 'gt_split_tf32x3')
+        sw = w.stride()
+        s_co, s_ci = (sw[1], sw[0]) if transpose else (sw[0], sw[1])
+        wp = torch.empty([kh * kw, cout, 3 * cin], dtype=torch.float32, device=x.device)
+        _lib.check(lib.gt_conv_pack_weight_tf32x3(_lib.ptr(w), s_co, s_ci, sw[2], sw[3], cout, cin, kh, kw, _lib.ptr(wp), st), 'gt_conv_pack_weight_tf32x3')
+        y = torch.empty([N, cout, OH, OW], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        if y.stride(1) != 1 or y.stride(3) != cout:            # size-1 dims can leave ambiguous strides; force NHWC
+            y = torch.empty([N, OH, OW, cout], dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+        c3 = 3 * cin
+        _lib.check(lib.gt_conv2d_igemm_tf32(_lib.ptr(xs), H * W * c3, W * c3, c3, _lib.ptr(wp), _lib.ptr(y), OH * OW * cout, OW * cout, cout,
+                                            N, H, W, c3, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0, st),
+                   'gt_conv2d_igemm_tf32')
+        _lib.count_launch(3)
+    return y
+
+
 def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, packed=None):
+    if covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
+        return igemm_forward_tf32x3(x, w, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
     if not covered(x, w, transpose, output_padding, stride, padding, groups):
         return None
     lib = _lib.load()

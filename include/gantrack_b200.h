@@ -95,6 +95,22 @@ int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long
                         long long ys_n, long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                         int KH, int KW, int stride, int pad, int transposed, void* stream);
 
+/* ---- fp32 convolutions on the tensor cores (3 x TF32) ------------------------------------------------------------------
+ * For the fp32 blocks of the networks (true-fp32 accuracy required; the reference runs them on cuDNN with TF32 off,
+ * S3/training/training_loop_mi_multimodal.py:169-170).  Each fp32 value v is split into big = rna_tf32(v) and
+ * small = rna_tf32(v - big); x*w ~= xb*wb + xb*ws + xs*wb is ONE TF32 convolution over a 3x wider channel dimension:
+ *   gt_split_tf32x3:             x [N,C,H,W] (any element strides)  -> out [N,H,W,3C] = [big | big | small]
+ *   gt_conv_pack_weight_tf32x3:  w (strided, like gt_conv_pack_weight_f16) -> out [KH*KW][Cout][3*Cin] = [big | small | big]
+ *   gt_conv2d_igemm_tf32:        same contract as gt_conv2d_igemm_f16 with fp32 tensors consumed as TF32 (Cin a multiple
+ *                                of 32 -- pass 3*C -- fp32 NHWC output); same kernels, kind::tf32. */
+int gt_split_tf32x3(const void* x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C, int H, int W, void* out,
+                    void* stream);
+int gt_conv_pack_weight_tf32x3(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin, int KH,
+                               int KW, void* out, void* stream);
+int gt_conv2d_igemm_tf32(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                         long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
+                         int stride, int pad, int transposed, void* stream);
+
 /* Weight gradient of the same convolutions (replaces cuDNN wgrad reached through autograd of F.conv2d /
  * F.conv_transpose2d, OPS/conv2d_gradfix.py:37-45).  U is the operand walked pixel by pixel, S the operand read at
  * shifted / strided positions:

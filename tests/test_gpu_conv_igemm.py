@@ -124,3 +124,54 @@ def test_conv_backend_routes_fp16_path_shapes_to_igemm():
     assert conv_backend.stats['igemm'] - before['igemm'] == 2            # forward + dgrad
     assert conv_backend.stats['igemm_wgrad'] - before['igemm_wgrad'] == 1
     assert conv_backend.stats['library'] == before['library']
+
+
+# fp32 layers on the tensor cores as 3 x TF32 (csrc/conv_igemm.cu: gt_split_tf32x3, gt_conv_pack_weight_tf32x3, gt_conv2d_igemm_tf32)
+FP32_CASES = [
+    ('fp32_3x3_p1_512_512_4', 8, 512, 512, 4, 4, 3, 1, 1, False),
+    ('fp32_3x3_p1_512_512_16', 4, 512, 512, 16, 16, 3, 1, 1, False),
+    ('fp32_3x3_p1_64_128_19', 3, 64, 128, 19, 19, 3, 1, 1, False),
+    ('fp32_3x3_T_s2_512_512_8', 4, 512, 512, 8, 8, 3, 2, 0, True),
+    ('fp32_3x3_s2_128_64_17', 3, 128, 64, 17, 17, 3, 2, 0, False),
+    ('fp32_1x1_96_64_8', 5, 96, 64, 8, 8, 1, 1, 0, False),
+    ('fp32_3x3_T_s1_p1_32_64_16', 2, 32, 64, 16, 16, 3, 1, 1, True),
+]
+
+
+@pytest.mark.parametrize('case', FP32_CASES, ids=lambda c: c[0])
+def test_fp32_conv_3xtf32_accuracy(case):
+    """The opt-in 3 x TF32 route for fp32 layers against a float64 reference.  Products are fp32-accurate; what remains is the
+    tensor core's truncating fp32 accumulation, linear in the number of K = 8 accumulator updates (taps * 3 * Cin / 8):
+    <= 1e-5 relative (the north star's fp32 bound) up to ~450 updates, <= 1e-4 for the 512-channel 3x3 layers -- which is why
+    the route is OFF by default (conv_igemm.tf32x3_enabled) and those layers keep the library's true-fp32 kernels."""
+    from gan_track_b200.torch_utils.ops import conv2d_gradfix, conv_backend, conv_igemm
+    _, N, ci, co, H, W, k, s, p, tr = case
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn([N, ci, H, W], device='cuda', generator=g).requires_grad_(True)
+    wshape = [ci, co, k, k] if tr else [co, ci, k, k]
+    w = (torch.randn(wshape, device='cuda', generator=g) / (ci * k * k) ** 0.5).requires_grad_(True)
+    fn = conv2d_gradfix.conv_transpose2d if tr else conv2d_gradfix.conv2d
+    before = dict(conv_backend.stats)
+    y0 = fn(x, w, stride=s, padding=p)
+    assert conv_backend.stats['library'] - before['library'] == 1, 'fp32 layers take the library route by default'
+    old_flag = conv_igemm.tf32x3_enabled
+    conv_igemm.tf32x3_enabled = True
+    try:
+        before = dict(conv_backend.stats)
+        y = fn(x, w, stride=s, padding=p)
+        dy = torch.randn(y.shape, device='cuda', generator=g)
+        dx, = torch.autograd.grad(y, [x], dy)
+        assert conv_backend.stats['igemm'] - before['igemm'] == 2, 'forward and data gradient must take the tensor-core route'
+    finally:
+        conv_igemm.tf32x3_enabled = old_flag
+    xr, wr = x.detach().double().requires_grad_(True), w.detach().double()
+    ref = F.conv_transpose2d(xr, wr, stride=s, padding=p) if tr else F.conv2d(xr, wr, stride=s, padding=p)
+    rdx, = torch.autograd.grad(ref, [xr], dy.double())
+    updates = k * k * 3 * max(ci, co) // 8
+    tol = 1e-5 if updates <= 450 else 1e-4
+    assert y.dtype == torch.float32 and y.shape == ref.shape
+
+    def rel64(a, b):
+        return float((a.detach().double() - b.detach()).abs().max() / b.detach().abs().max())
+    assert rel64(y, ref) <= tol and rel64(dx, rdx) <= tol
+    assert rel64(y0, ref) <= 1e-4
