@@ -46,6 +46,7 @@ _PROTOTYPES = {
     'gt_split_tf32x3': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
     'gt_conv_pack_weight_tf32x3': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
     'gt_conv2d_igemm_tf32': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'gt_conv2d_igemm_f16_bias_act': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp]),
     'gt_conv2d_wgrad_workspace': (_ll, [_i, _i, _i, _i, _i, _i, _i]),
     'gt_conv2d_wgrad_f16': (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _ll, _vp, _ll, _vp]),
 }

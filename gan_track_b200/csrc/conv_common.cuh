@@ -3,6 +3,7 @@
 #pragma once
 #include "gt_common.cuh"
 #include "gt_sm100.cuh"
+#include "hot_act.cuh"
 
 constexpr int CONV_MAX_TAPS = 9;
 constexpr int CONV_MAX_PHASES = 4;
@@ -27,32 +28,54 @@ struct ConvParams {
     void* y;                         // fp16 (tf32 == 0) or fp32 (tf32 == 1) NHWC output
     long long ys_n, ys_h, ys_w;      // element strides
     int tf32;                        // 1: operands are fp32 bit patterns consumed as TF32 (32 channels per 128-byte chunk), fp32 output
+    // optional fused epilogue (fp16 output only): y = clamp(act(round_fp16(acc) + bias[co]) * gain), the bias_act that follows the
+    // convolution in Conv2dLayer.forward (S3/training/networks_stylegan2.py:176-177); ep_act 0 = plain store
+    const __half* ep_bias;
+    int ep_act;
+    float ep_alpha, ep_gain, ep_clamp;
     // halo kernel only
     int dy_min[CONV_MAX_PHASES], dx_min[CONV_MAX_PHASES];   // most negative tap offset of the phase = halo origin
     int halo_w, halo_h;                                      // TMA box extent in pixels
 };
 
-// 32 consecutive accumulator columns of one output pixel -> global memory (fp16: 64 bytes, fp32: 128 bytes)
-__device__ __forceinline__ void conv_store32(void* y, long long elem_off, int tf32, const uint32_t (&r)[32]) {
-    if (tf32) {
-        float* yp = (float*)y + elem_off;
+// 32 consecutive accumulator columns (output channels co0 .. co0+31) of one output pixel -> global memory
+// (fp16: 64 bytes, fp32: 128 bytes), through the optional bias + activation epilogue
+__device__ __forceinline__ void conv_store32(const ConvParams& p, long long elem_off, int co0, const uint32_t (&r)[32]) {
+    if (p.tf32) {
+        float* yp = (float*)p.y + elem_off;
 #pragma unroll
         for (int v = 0; v < 8; v++) *reinterpret_cast<uint4*>(yp + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
-    } else {
-        __half* yp = (__half*)y + elem_off;
+        return;
+    }
+    __half* yp = (__half*)p.y + elem_off;
+    const bool ep = p.ep_act != 0;
+    const hot::Params hp = hot::make_params(p.ep_alpha, p.ep_gain, p.ep_clamp);
+    const bool clamp_on = p.ep_clamp >= 0.f;
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            uint4 o;
-            __half2 h0 = __floats2half2_rn(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-            __half2 h1 = __floats2half2_rn(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-            __half2 h2 = __floats2half2_rn(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-            __half2 h3 = __floats2half2_rn(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
-            o.x = *reinterpret_cast<uint32_t*>(&h0);
-            o.y = *reinterpret_cast<uint32_t*>(&h1);
-            o.z = *reinterpret_cast<uint32_t*>(&h2);
-            o.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(yp + v * 8) = o;
+    for (int v = 0; v < 4; v++) {
+        __half2 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(__uint_as_float(r[v * 8 + 2 * k]), __uint_as_float(r[v * 8 + 2 * k + 1]));
+        if (ep) {
+            // the reference materialises the convolution output in fp16 before bias_act reads it back: round first
+            Vec16<__half> bv;
+            if (p.ep_bias) bv = ld16(p.ep_bias + co0 + v * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float2 u = __half22float2(h[k]);
+                if (p.ep_bias) u = __fadd2_rn(u, __half22float2(reinterpret_cast<const __half2*>(bv.v)[k]));
+                float2 o;
+                if (p.ep_act == hot::LRELU) o = clamp_on ? hot::fwd<hot::LRELU, true>(u, hp) : hot::fwd<hot::LRELU, false>(u, hp);
+                else o = clamp_on ? hot::fwd<hot::LINEAR, true>(u, hp) : hot::fwd<hot::LINEAR, false>(u, hp);
+                h[k] = __float22half2_rn(o);
+            }
         }
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        o.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        o.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        o.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        *reinterpret_cast<uint4*>(yp + v * 8) = o;
     }
 }
 

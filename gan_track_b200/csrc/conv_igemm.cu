@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
             tmem_ld_wait();
-            if (valid) conv_store32(p.y, yoff + c * 32, p.tf32, r);
+            if (valid) conv_store32(p, yoff + c * 32, nt * BN + c * 32, r);
         }
     }
     tc_fence_before();
@@ -251,8 +251,11 @@ extern "C" int gt_conv_pack_weight_f16(const void* w, long long s_co, long long 
 
 static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
                              long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
-                             int pad, int transposed, int tf32, void* stream) {
+                             int pad, int transposed, int tf32, const void* ep_bias, int ep_act, float ep_alpha, float ep_gain, float ep_clamp,
+                             void* stream) {
     const int esz = tf32 ? 4 : 2, kel = tf32 ? 32 : BK, al = 16 / esz;
+    GT_REQUIRE(ep_act == 0 || (!tf32 && (ep_act == 1 || ep_act == 3)), "gt_conv2d_igemm: fused epilogue supports fp16 output with linear (1) or lrelu (3); got %d", ep_act);
+    GT_REQUIRE(ep_bias == nullptr || (((uintptr_t)ep_bias) & 15) == 0, "gt_conv2d_igemm: epilogue bias must be 16-byte aligned");
     GT_REQUIRE(x && wpacked && y, "gt_conv2d_igemm_f16: null pointer");
     GT_REQUIRE(N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "gt_conv2d_igemm_f16: empty tensor");
     GT_REQUIRE(Cin % kel == 0 && Cout % 64 == 0, "gt_conv2d_igemm: Cin (%d) must be a multiple of %d and Cout (%d) of 64", Cin, kel, Cout);
@@ -270,6 +273,11 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     p.Cout = Cout;
     p.y = y;
     p.tf32 = tf32;
+    p.ep_bias = (const __half*)ep_bias;
+    p.ep_act = ep_act;
+    p.ep_alpha = ep_alpha;
+    p.ep_gain = ep_gain;
+    p.ep_clamp = ep_clamp;
     p.ys_n = ys_n;
     p.ys_h = ys_h;
     p.ys_w = ys_w;
@@ -384,7 +392,18 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
 extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
                                    long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
                                    int pad, int transposed, void* stream) {
-    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, stream);
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, nullptr, 0,
+                             0.f, 1.f, -1.f, stream);
+}
+
+// the same convolution with the layer's bias_act fused into the epilogue: y = clamp(act(conv + bias) * gain)
+extern "C" int gt_conv2d_igemm_f16_bias_act(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                                            long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
+                                            int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain, float clamp,
+                                            void* stream) {
+    GT_REQUIRE(act == 1 || act == 3, "gt_conv2d_igemm_f16_bias_act: act must be linear (1) or lrelu (3); got %d", act);
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, bias, act,
+                             alpha, gain, clamp, stream);
 }
 
 // ---- fp32 convolutions on the tensor cores: 3 x TF32 ------------------------------------------------------------------
@@ -470,5 +489,6 @@ extern "C" int gt_conv_pack_weight_tf32x3(const void* w, long long s_co, long lo
 extern "C" int gt_conv2d_igemm_tf32(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
                                     long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
                                     int pad, int transposed, void* stream) {
-    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 1, stream);
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 1, nullptr, 0,
+                             0.f, 1.f, -1.f, stream);
 }

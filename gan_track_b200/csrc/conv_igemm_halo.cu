@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c * 32), r);
                     tmem_ld_wait();
-                    if (valid) conv_store32(p.y, yoff + c * 32, p.tf32, r);
+                    if (valid) conv_store32(p, yoff + c * 32, it.nt * BN + c * 32, r);
                 }
             }
             tc_fence_before();

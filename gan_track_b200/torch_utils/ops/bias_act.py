@@ -149,5 +149,7 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
                 d_b = d_x.sum([i for i in range(d_x.ndim) if i != dim])
             return d_dy, d_x, d_b, None
 
+    BiasActCuda.Grad = BiasActCudaGrad          # used by the fused conv + bias_act op (conv2d_gradfix.conv2d_bias_act)
+    BiasActCuda.cfg = (spec, alpha, gain, clamp, trivial)
     _cache[key] = BiasActCuda
     return BiasActCuda

@@ -120,9 +120,92 @@ def _conv_fn(transpose, weight_shape, stride, padding, output_padding, groups):
                 assert d_x.shape == ctx.x_shape
             return d_dy, d_x
 
+    Conv2d.GradWeight = Conv2dGradWeight
+    Conv2d.grad_output_padding = staticmethod(grad_output_padding)
     _cache[key] = Conv2d
     return Conv2d
 
 
 def _empty(like):
     return torch.empty([0], dtype=like.dtype, device=like.device)
+
+
+# ---- convolution with the layer's bias_act fused into the kernel epilogue ----------------------------------------------
+
+_ACT_CODE = {'linear': 1, 'lrelu': 3}
+import os as _os
+fuse_bias_act = _os.environ.get('GT_FUSE_BIAS_ACT', '1') != '0'      # False: always conv followed by a separate bias_act pass
+
+
+def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, clamp=None, stride=1, padding=0):
+    """clamp(act(conv2d(input, weight) + bias) * gain), the tail of Conv2dLayer.forward (S3/training/networks_stylegan2.py:173-177).
+    When the tcgen05 kernel takes the convolution (fp16 channels-last, channels multiples of 64) the bias / activation /
+    gain / clamp run in its epilogue -- the activation tensor is written once instead of written, re-read and re-written --
+    otherwise this is exactly `bias_act(conv2d(...))`.  Gradients of any order: backward = bias_act's gradient Function
+    followed by the convolution's, both differentiable."""
+    from . import bias_act as bias_act_mod
+    from . import conv_igemm
+    stride, padding = _pair(stride), _pair(padding)
+    fusable = (fuse_bias_act and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
+               and conv_igemm.covered(input, weight, False, (0, 0), stride, padding, 1) and (bias is None or bias.numel() % 8 == 0))
+    if not fusable:
+        y = conv2d(input, weight, stride=stride, padding=padding)
+        return bias_act_mod.bias_act(y, bias, act=act, alpha=alpha, gain=gain, clamp=clamp)
+    bias_act_mod._init()
+    BA = bias_act_mod._bias_act_cuda(dim=1, act=act, alpha=alpha, gain=gain, clamp=clamp)
+    spec, alpha_f, gain_f, clamp_f, trivial = BA.cfg
+    Conv = _conv_fn(False, tuple(weight.shape), stride, padding, (0, 0), 1)
+    return _fused_fn(Conv, BA, stride, padding).apply(input, weight, bias)
+
+
+_fused_cache = dict()
+
+
+def _fused_fn(Conv, BA, stride, padding):
+    key = (Conv, BA)
+    if key in _fused_cache:
+        return _fused_cache[key]
+    from . import bias_act as bias_act_mod
+    from . import conv_igemm
+    spec, alpha, gain, clamp, trivial = BA.cfg
+
+    class ConvBiasAct(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, b):
+            bb = b.to(torch.float16).contiguous() if b is not None else None
+            y = conv_igemm.igemm_forward(x, w, transpose=False, output_padding=(0, 0), stride=stride, padding=padding, groups=1,
+                                         epilogue=(bb, spec.cuda_idx, alpha, gain, clamp))
+            assert y is not None
+            conv_backend.stats['igemm'] += 1
+            # like the reference's bias_act, `linear` saves no output (callers may then update it in place, e.g. y.add_(x) in
+            # DiscriminatorBlock.forward, S3/training/networks_stylegan2.py:636)
+            ctx.save_for_backward(x if w.requires_grad else _empty(x), w, y if 'y' in spec.ref else _empty(y))
+            ctx.x_shape = x.shape
+            ctx.has_bias = b is not None
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, w, y = ctx.saved_tensors
+            dx = dw = db = None
+            want_db = ctx.has_bias and ctx.needs_input_grad[2]
+            dy = dy.contiguous(memory_format=torch.channels_last)
+            # gradient of bias_act from the saved OUTPUT (lrelu / linear need nothing else, OPS/bias_act.py:151-154)
+            # (`linear` saves no output in the reference, so its clamp does not mask the gradient: pass y only where the reference does)
+            ysave = y if y.numel() else None
+            if want_db and not torch.is_grad_enabled():
+                dpre, db = bias_act_mod._fused_bwd(dy, ysave, 1, spec, alpha, gain, clamp)      # dx and db in one pass
+            else:
+                e = bias_act_mod._empty
+                dpre = dy if trivial else BA.Grad.apply(dy, e, e, ysave if ysave is not None else e)
+                if want_db:
+                    db = dpre.sum([0, 2, 3])
+            if ctx.needs_input_grad[0]:
+                op = Conv.grad_output_padding(ctx.x_shape, dpre.shape)
+                dx = _conv_fn(True, tuple(w.shape), stride, padding, op, 1).apply(dpre, w)
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                dw = Conv.GradWeight.apply(dpre, x)
+            return dx, dw, db
+
+    _fused_cache[key] = ConvBiasAct
+    return ConvBiasAct

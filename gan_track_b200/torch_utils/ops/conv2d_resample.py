@@ -20,17 +20,24 @@ def _get_weight_shape(w):
     return [int(sz) for sz in w.shape]
 
 
-def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True):
-    """conv2d / conv_transpose2d; `flip_weight=False` means true convolution (taps reversed)."""
+def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True, epilogue=None):
+    """conv2d / conv_transpose2d; `flip_weight=False` means true convolution (taps reversed).  `epilogue`: dict(b, act, gain,
+    clamp) -- the bias_act that follows the convolution, fused into the kernel where it can be (conv2d_gradfix.conv2d_bias_act)."""
     _oc, _icg, kh, kw = _get_weight_shape(w)
     if not flip_weight and (kw > 1 or kh > 1):
         w = w.flip([2, 3])
+    if epilogue is not None:
+        assert not transpose and groups == 1
+        return conv2d_gradfix.conv2d_bias_act(x, w, epilogue['b'], act=epilogue['act'], gain=epilogue['gain'], clamp=epilogue['clamp'],
+                                              stride=stride, padding=padding)
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
     return op(x, w, stride=stride, padding=padding, groups=groups)
 
 
 @misc.profiled_function
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, epilogue=None):
+    """`epilogue` (not in the reference): dict(b, act, gain, clamp) applied as bias_act to the result; only accepted when the
+    convolution is the LAST kernel of the case split (up == 1, groups == 1), where it is fused into the convolution."""
     assert isinstance(x, torch.Tensor) and x.ndim == 4
     assert isinstance(w, torch.Tensor) and w.ndim == 4 and w.dtype == x.dtype
     assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)
@@ -53,10 +60,11 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         py0 += (fh - down + 1) // 2
         py1 += (fh - down) // 2
 
+    assert epilogue is None or (up == 1 and groups == 1), 'a fused epilogue needs the convolution to be the last kernel'
     pointwise = (kw == 1 and kh == 1)
     if pointwise and down > 1 and up == 1:          # decimate first: the 1x1 conv then sees 1/4 of the pixels
         x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, padding=[px0, px1, py0, py1], flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
+        return _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight, epilogue=epilogue)
 
     if pointwise and up > 1 and down == 1:          # convolve first: the 1x1 conv sees the small image
         x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
@@ -64,7 +72,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
 
     if down > 1 and up == 1:                        # blur, then strided conv
         x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0, px1, py0, py1], flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight)
+        return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight, epilogue=epilogue)
 
     if up > 1:                                      # transposed strided conv, then blur (and optional decimation)
         if groups == 1:
@@ -84,11 +92,14 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         return x
 
     if up == 1 and down == 1 and px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:
-        return _conv2d_wrapper(x=x, w=w, padding=[py0, px0], groups=groups, flip_weight=flip_weight)
+        return _conv2d_wrapper(x=x, w=w, padding=[py0, px0], groups=groups, flip_weight=flip_weight, epilogue=epilogue)
 
     # Anything else: explicit pad/upsample, conv, decimate.
     x = upfirdn2d.upfirdn2d(x=x, f=(f if up > 1 else None), up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
     x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
     if down > 1:
         x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
+    if epilogue is not None:
+        from . import bias_act
+        x = bias_act.bias_act(x, epilogue['b'], act=epilogue['act'], gain=epilogue['gain'], clamp=epilogue['clamp'])
     return x

@@ -113,8 +113,10 @@ def igemm_forward_tf32x3(x, w, *, transpose, output_padding, stride, padding, gr
     return y
 
 
-def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, packed=None):
-    if covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
+def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, packed=None, epilogue=None):
+    """epilogue: None, or (bias fp16 [Cout] or None, act code 1 / 3, alpha, gain, clamp) -- the layer's bias_act fused into
+    the kernel's epilogue (fp16 only; the caller checks `covered` first)."""
+    if epilogue is None and covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
         return igemm_forward_tf32x3(x, w, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
     if not covered(x, w, transpose, output_padding, stride, padding, groups):
         return None
@@ -131,9 +133,15 @@ def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, p
             packed = pack_weight(w, transpose)
         y = torch.empty([N, cout, OH, OW], dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
         ys_n, ys_h, ys_w = OH * OW * cout, OW * cout, cout
-        _lib.check(lib.gt_conv2d_igemm_f16(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,
-                                           N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0, _lib.stream_of(x)),
-                   'gt_conv2d_igemm_f16')
+        if epilogue is None:
+            _lib.check(lib.gt_conv2d_igemm_f16(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,
+                                               N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0, _lib.stream_of(x)),
+                       'gt_conv2d_igemm_f16')
+        else:
+            b, act, alpha, gain, clamp = epilogue
+            _lib.check(lib.gt_conv2d_igemm_f16_bias_act(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,
+                                                        N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0,
+                                                        _lib.ptr(b), act, alpha, gain, clamp, _lib.stream_of(x)), 'gt_conv2d_igemm_f16_bias_act')
         _lib.count_launch()
     return y
 

@@ -154,9 +154,13 @@ class Conv2dLayer(torch.nn.Module):
     def forward(self, x, gain=1):
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None
+        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        if self.up == 1 and x.is_cuda and self.activation in ('linear', 'lrelu'):
+            # the convolution is the last kernel of conv2d_resample: its bias_act rides in the convolution's epilogue
+            return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,
+                                                   flip_weight=True, epilogue=dict(b=b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp))
         x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
                                             padding=self.padding, flip_weight=(self.up == 1))
-        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return bias_act.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
 
     def extra_repr(self):

@@ -94,6 +94,13 @@ int gt_conv_pack_weight_f16(const void* w, long long s_co, long long s_ci, long 
 int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y,
                         long long ys_n, long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                         int KH, int KW, int stride, int pad, int transposed, void* stream);
+/* The same convolution with the layer's bias_act fused into the epilogue (Conv2dLayer.forward,
+ * S3/training/networks_stylegan2.py:173-177): y = clamp(act(round_fp16(conv) + bias[co]) * gain); act 1 = linear, 3 = lrelu;
+ * bias: [Cout] fp16 or NULL; clamp < 0 disables clamping. */
+int gt_conv2d_igemm_f16_bias_act(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y,
+                                 long long ys_n, long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                                 int KH, int KW, int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain,
+                                 float clamp, void* stream);
 
 /* ---- fp32 convolutions on the tensor cores (3 x TF32) ------------------------------------------------------------------
  * For the fp32 blocks of the networks (true-fp32 accuracy required; the reference runs them on cuDNN with TF32 off,
