@@ -43,18 +43,32 @@ __global__ void __launch_bounds__(256) fc_fwd_kernel(const float* __restrict__ x
     float acc[MB];
 #pragma unroll
     for (int m = 0; m < MB; m++) acc[m] = 0.f;
-    for (int k0 = 0; k0 < I; k0 += FC_KC) {
-        // the weight vector of this chunk is requested first so that its latency overlaps the staging of x
-        const int k = k0 + lane * 4;
-        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < O && k < I) wv = *reinterpret_cast<const float4*>(w + (long long)o * I + k);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < MB * (FC_KC / 4); idx += 256) {
+    // software pipeline: the x chunk and the weight vector of round r+1 are in flight (registers) while round r is consumed
+    constexpr int XPT = MB * (FC_KC / 4) / 256;        // float4 of x per thread per chunk
+    float4 xpre[XPT];
+    float4 wpre;
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < XPT; j++) {
+            const int idx = threadIdx.x + j * 256;
             const int m = idx / (FC_KC / 4), q = idx - m * (FC_KC / 4);
             const int kk = k0 + q * 4;
-            xs[m][q] = (m < M && kk < I) ? *reinterpret_cast<const float4*>(x + (long long)m * I + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xpre[j] = (m < M && kk < I) ? *reinterpret_cast<const float4*>(x + (long long)m * I + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        const int k = k0 + lane * 4;
+        wpre = (o < O && k < I) ? *reinterpret_cast<const float4*>(w + (long long)o * I + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < I; k0 += FC_KC) {
         __syncthreads();
+#pragma unroll
+        for (int j = 0; j < XPT; j++) {
+            const int idx = threadIdx.x + j * 256;
+            xs[idx / (FC_KC / 4)][idx % (FC_KC / 4)] = xpre[j];
+        }
+        const float4 wv = wpre;
+        __syncthreads();
+        if (k0 + FC_KC < I) fetch(k0 + FC_KC);
 #pragma unroll
         for (int m = 0; m < MB; m++) {
             const float4 xv = xs[m][lane];
@@ -89,7 +103,7 @@ template <int MB>
 __global__ void __launch_bounds__(256) fc_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int M, int I,
                                                        int O, float wgain) {
     constexpr int OC = 128;                      // output features staged per round (16 weight loads in flight per thread)
-    __shared__ float dys[OC][MB];
+    __shared__ __align__(16) float dys[OC][MB];
     __shared__ float red[8][8][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 32 + lane;
@@ -107,14 +121,23 @@ __global__ void __launch_bounds__(256) fc_dgrad_kernel(const float* __restrict__
         __syncthreads();
         for (int idx = threadIdx.x; idx < OC * MB; idx += 256) {
             const int m = idx / OC, oo = idx - m * OC;         // consecutive threads -> consecutive o: coalesced reads of dy[m, :]
-            dys[oo][m] = (m < M && o0 + oo < O) ? dy[(long long)m * O + o0 + oo] : 0.f;
+            // rows of dys are MB floats apart, so a plain [oo][m] store would put all 32 lanes on one bank; XOR the 4-float
+            // group index with the row (groups of 4 m stay contiguous for the 16-byte reads below)
+            dys[oo][m ^ (((oo & (MB / 4 - 1))) << 2)] = (m < M && o0 + oo < O) ? dy[(long long)m * O + o0 + oo] : 0.f;
         }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < OC / 8; j++) {
             const int oo = warp + 8 * j;
+            const int sw = (oo & (MB / 4 - 1)) << 2;
 #pragma unroll
-            for (int m = 0; m < MB; m++) acc[m] += dys[oo][m] * wv[j];
+            for (int m4 = 0; m4 < MB; m4 += 4) {
+                const float4 d4 = *reinterpret_cast<const float4*>(&dys[oo][m4 ^ sw]);
+                acc[m4 + 0] += d4.x * wv[j];
+                acc[m4 + 1] += d4.y * wv[j];
+                acc[m4 + 2] += d4.z * wv[j];
+                acc[m4 + 3] += d4.w * wv[j];
+            }
         }
     }
     // combine the 8 warps in warp order, 8 rows at a time (keeps the scratch at 8.4 KB for any MB)
