@@ -39,6 +39,9 @@ _PROTOTYPES = {
     'gt_fc_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     'gt_fc_dgrad': (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'gt_fc_wgrad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    'gt_adam_chunk_bytes': (_i, []),
+    'gt_adam_flat': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _vp]),
+    'gt_ema_flat': (_i, [_vp, _vp, _ll, _f, _vp]),
     'gt_conv_igemm_config': (_i, [_i]),
     'gt_conv_wgrad_config': (_i, [_i]),
     'gt_conv_pack_weight_f16': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),

@@ -33,6 +33,7 @@ from .. import dnnlib
 from ..torch_utils import misc, training_stats
 from ..torch_utils.ops import conv2d_gradfix, grid_sample_gradfix
 from . import augment as augment_mod
+from . import flat_optim
 from . import loss as loss_mod
 from . import networks_stylegan2 as networks
 
@@ -215,6 +216,10 @@ class Trainer:
                         torch.distributed.broadcast(t, src=0)
         self.loss = loss_mod.StyleGAN2Loss(device=dev, G=self.G, D=self.D, augment_pipe=self.augment_pipe, **cfg.loss_kwargs)
 
+        # Graph mode: parameters live in flat buffers; gradient scrub + Adam and the G_ema lerp are single kernels (csrc/optim.cu)
+        self.flat = None
+        if self.use_graphs:
+            self.flat = dnnlib.EasyDict(G=flat_optim.FlatParams(self.G), D=flat_optim.FlatParams(self.D), G_ema=flat_optim.FlatParams(self.G_ema))
         self.phases = []
         for name, module, opt_kwargs, reg_interval in [('G', self.G, cfg.G_opt_kwargs, cfg.G_reg_interval), ('D', self.D, cfg.D_opt_kwargs, cfg.D_reg_interval)]:
             params = list(module.parameters())
@@ -223,6 +228,8 @@ class Trainer:
             if reg_interval is None:
                 opt = torch.optim.Adam(params, **opt_kwargs, **adam_extra)
                 self.phases.append(dnnlib.EasyDict(name=name + 'both', module=module, opt=opt, interval=1, reducer=reducer, grad_set=None))
+                if self.flat is not None:
+                    self.phases[-1].flat_opt = flat_optim.FlatAdam(self.flat[name], lr=opt_kwargs['lr'], betas=opt_kwargs['betas'], eps=opt_kwargs['eps'])
             else:
                 ratio = reg_interval / (reg_interval + 1)
                 kw = dict(opt_kwargs)
@@ -231,6 +238,9 @@ class Trainer:
                 opt = torch.optim.Adam(params, **kw, **adam_extra)
                 self.phases.append(dnnlib.EasyDict(name=name + 'main', module=module, opt=opt, interval=1, reducer=reducer, grad_set=None))
                 self.phases.append(dnnlib.EasyDict(name=name + 'reg', module=module, opt=opt, interval=reg_interval, reducer=reducer, grad_set=None))
+                if self.flat is not None:
+                    fopt = flat_optim.FlatAdam(self.flat[name], lr=kw['lr'], betas=kw['betas'], eps=kw['eps'])
+                    self.phases[-1].flat_opt = self.phases[-2].flat_opt = fopt
         self.cur_nimg = 0
         self.batch_idx = 0
         self.time_phases = False          # bench.py: CUDA-event time of every graphed phase replay (read with phase_times())
@@ -282,9 +292,12 @@ class Trainer:
             ema_nimg = min(ema_nimg, self.cur_nimg * cfg.ema_rampup)
         ema_beta = 0.5 ** (cfg.batch_size / max(ema_nimg, 1e-8))
         with torch.no_grad():
-            g_params = list(self.G.parameters())
-            e_params = list(self.G_ema.parameters())
-            torch._foreach_lerp_(e_params, g_params, 1.0 - ema_beta)            # p_ema = p.lerp(p_ema, beta)
+            if self.flat is not None:
+                flat_optim.ema_update(self.flat.G_ema, self.flat.G, 1.0 - ema_beta)    # one launch over the flat buffers
+            else:
+                g_params = list(self.G.parameters())
+                e_params = list(self.G_ema.parameters())
+                torch._foreach_lerp_(e_params, g_params, 1.0 - ema_beta)            # p_ema = p.lerp(p_ema, beta)
             for b_ema, b in zip(self.G_ema.buffers(), self.G.buffers()):
                 b_ema.copy_(b)
 
@@ -320,9 +333,14 @@ class Trainer:
                                        gain=phase.interval, cur_nimg=self.cur_nimg)
         phase.module.requires_grad_(False)
         st.with_grad = [p for p in phase.module.parameters() if p.grad is not None]
+        st.active_idx = [i for i, p in enumerate(phase.module.parameters()) if p.grad is not None]
         st.flat = torch.cat([p.grad.flatten() for p in st.with_grad])
 
     def _phase_half_b(self, phase, st):
+        if phase.get('flat_opt') is not None:
+            # /num_gpus, nan_to_num and Adam in one kernel over the flat gradient (parameters without a gradient are skipped)
+            phase.flat_opt.step(phase.name, st.active_idx, st.flat, grad_scale=1.0 / self.num_gpus)
+            return
         flat = st.flat
         if self.num_gpus > 1:
             flat = flat / self.num_gpus

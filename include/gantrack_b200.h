@@ -146,6 +146,19 @@ int gt_fc_fwd(const float* x, const float* w, const float* b, float* y, int M, i
 int gt_fc_dgrad(const float* dy, const float* w, float* dx, int M, int I, int O, float wgain, void* stream);
 int gt_fc_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int I, int O, float wgain, float bgain, void* stream);
 
+/* ---- parameter update on flat buffers ------------------------------------------------------
+ * A module's parameters, gradients and Adam moments are views into flat fp32 buffers.  gt_adam_flat fuses the gradient
+ * exchange epilogue (x grad_scale = 1/num_gpus, nan_to_num(0, posinf, neginf)) with torch.optim.Adam's update
+ * (S3/training/training_loop_mi_multimodal.py:343-351 + opt.step()).  `chunks`: device array of records
+ * {int64 pstart; int64 gstart; int32 count; int32 seg} (gt_adam_chunk_bytes() each) that never straddle a parameter
+ * (pstart indexes p / m / v, gstart the phase's compact gradient buffer `grad`); `active[seg]` = 0 skips
+ * a parameter exactly like `grad is None` does; `steps[seg]` is the parameter's own step count (incremented here).
+ * gt_ema_flat: p_ema += weight * (p - p_ema), the G_ema update (:358-366) in one launch. */
+int gt_adam_chunk_bytes(void);
+int gt_adam_flat(float* p, float* grad, float* m, float* v, float* steps, const int* active, int nseg, const void* chunks, int nchunks,
+                 float lr, float beta1, float beta2, float eps, float grad_scale, float posinf, float neginf, void* stream);
+int gt_ema_flat(float* p_ema, const float* p, long long n, float weight, void* stream);
+
 /* ---- ADA geometric warp (fp32) ------------------------------------------------------------------------------------
  * Replaces the op sequence of S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps,
  * up=2) -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE

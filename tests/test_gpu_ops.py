@@ -365,3 +365,42 @@ def test_fc_linear_matches_addmm_to_second_order(M, I, O, bias):
     for a, c in zip(outs[0], outs[1]):
         assert a.shape == c.shape
         assert_close(a, c.cpu(), 2e-5, 'fc')
+
+
+# ---------------------------------------------------------------------------------------------------- flat Adam / EMA
+
+def test_flat_adam_and_ema_match_torch():
+    """csrc/optim.cu against torch.optim.Adam (+ /num_gpus and nan_to_num of the gradient exchange) over several steps in which
+    some parameters receive no gradient (they must be skipped: no moment decay, no step count), and torch._foreach_lerp_."""
+    import copy
+    from gan_track_b200.training import flat_optim
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 129), torch.nn.Conv2d(3, 5, 3), torch.nn.Linear(11, 7, bias=False)).to(DEV)
+    ref = copy.deepcopy(net)
+    ema, ema_ref = copy.deepcopy(net), copy.deepcopy(net)
+    kw = dict(lr=0.0025 * 0.8, betas=[0.0, 0.99 ** 0.8], eps=1e-8)
+    opt_ref = torch.optim.Adam(ref.parameters(), **kw)
+    fp, fe = flat_optim.FlatParams(net), flat_optim.FlatParams(ema)
+    opt = flat_optim.FlatAdam(fp, **kw)
+    params, rparams = list(net.parameters()), list(ref.parameters())
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, ref.state_dict()[k])                 # re-homing kept the values
+    for it in range(6):
+        active = [0, 1, 2, 3, 4] if it % 3 else [0, 2, 4]          # a "reg" phase touches fewer parameters
+        grads = [torch.randn_like(rparams[i]) * (10.0 ** (it % 3 - 1)) for i in active]
+        grads[0][0, 0] = float('nan')
+        grads[1].view(-1)[1] = float('inf')
+        for p in rparams:
+            p.grad = None
+        for i, g in zip(active, grads):
+            rparams[i].grad = torch.nan_to_num(g / 2, nan=0, posinf=1e5, neginf=-1e5)
+        opt_ref.step()
+        flat = torch.cat([g.flatten() for g in grads])
+        opt.step('main' if it % 3 else 'reg', active, flat, grad_scale=0.5)
+        with torch.no_grad():
+            torch._foreach_lerp_(list(ema_ref.parameters()), rparams, 0.03)
+        flat_optim.ema_update(fe, fp, 0.03)
+    for p, r in zip(params, rparams):
+        assert_close(p, r.detach().cpu(), 2e-6, 'adam param')
+    for p, r in zip(ema.parameters(), ema_ref.parameters()):
+        assert_close(p, r.detach().cpu(), 2e-6, 'ema param')
