@@ -42,6 +42,9 @@ _PROTOTYPES = {
     'gt_adam_chunk_bytes': (_i, []),
     'gt_adam_flat': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _vp]),
     'gt_ema_flat': (_i, [_vp, _vp, _ll, _f, _vp]),
+    'gt_fromrgb1_bwd_workspace': (_ll, [_i]),
+    'gt_fromrgb1_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _ll, _i, _vp]),
+    'gt_fromrgb1_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _ll, _i, _vp]),
     'gt_conv_igemm_config': (_i, [_i]),
     'gt_conv_wgrad_config': (_i, [_i]),
     'gt_conv_pack_weight_f16': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..torch_utils import misc
-from ..torch_utils.ops import bias_act, conv2d_resample, fc, fma, modulated, upfirdn2d
+from ..torch_utils.ops import bias_act, conv2d_resample, fc, fma, modulated, rgb, upfirdn2d
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -155,6 +155,11 @@ class Conv2dLayer(torch.nn.Module):
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        if (self.in_channels == 1 and self.weight.shape[2] == 1 and self.up == 1 and self.down == 1 and self.activation in ('linear', 'lrelu')
+                and rgb.applicable(x, self.out_channels)):
+            # FromRGB on single-channel slices: outer product + bias_act in one pass, written channels-last (csrc/rgb.cu)
+            y = rgb.fromrgb1(x, w.to(x.dtype).reshape(-1), b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
+            return y
         if self.up == 1 and x.is_cuda and self.activation in ('linear', 'lrelu'):
             # the convolution is the last kernel of conv2d_resample: its bias_act rides in the convolution's epilogue
             return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,

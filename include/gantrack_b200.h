@@ -159,6 +159,18 @@ int gt_adam_flat(float* p, float* grad, float* m, float* v, float* steps, const 
                  float lr, float beta1, float beta2, float eps, float grad_scale, float posinf, float neginf, void* stream);
 int gt_ema_flat(float* p_ema, const float* p, long long n, float weight, void* stream);
 
+/* ---- FromRGB with ONE image channel ----------------------------------------------------------------------------------
+ * Conv2dLayer(1 -> C, kernel 1) + bias_act of the discriminator's top block (S3/training/networks_stylegan2.py:586, 617-621) as
+ * one pass, written channels-last: y[n,p,c] = clamp(act(round_T(x[n,p] * w[c]) + b[c]) * gain).  x: [N*P] T, w / b: [C] T
+ * (b may be NULL), y / dy: [N*P, C] T; C/vec a power of two <= 32.  gt_fromrgb1_bwd: g1 = dy * gain * act'(y) * [|y| < clamp];
+ * dw[c] = sum g1 x; db[c] = sum g1 (fp32); dx[n,p] = sum_c g1 w[c] (dx may be NULL); workspace: gt_fromrgb1_bwd_workspace(C) floats. */
+long long gt_fromrgb1_bwd_workspace(int C);
+int gt_fromrgb1_fwd(const void* x, const void* w, const void* b, void* y, int dtype, int act, float alpha, float gain, float clamp,
+                    long long NP, int C, void* stream);
+int gt_fromrgb1_bwd(const void* dy, const void* y, const void* x, const void* w, void* dx, float* dw, float* db, float* workspace,
+                    long long workspace_floats, int dtype, int act, float alpha, float gain, float clamp, long long NP, int C,
+                    void* stream);
+
 /* ---- ADA geometric warp (fp32) ------------------------------------------------------------------------------------
  * Replaces the op sequence of S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps,
  * up=2) -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE

@@ -404,3 +404,37 @@ def test_flat_adam_and_ema_match_torch():
         assert_close(p, r.detach().cpu(), 2e-6, 'adam param')
     for p, r in zip(ema.parameters(), ema_ref.parameters()):
         assert_close(p, r.detach().cpu(), 2e-6, 'ema param')
+
+
+# ---------------------------------------------------------------------------------------------------- FromRGB (1 channel)
+
+@pytest.mark.parametrize('dtype,C,act,clamp', [(torch.float16, 64, 'lrelu', 256.0), (torch.float16, 128, 'lrelu', 0.5), (torch.float32, 16, 'lrelu', None),
+                                               (torch.float16, 8, 'linear', 1.0)])
+def test_fromrgb1_matches_conv_bias_act(dtype, C, act, clamp):
+    """csrc/rgb.cu against the reference's op sequence conv2d (1x1, one input channel) + bias_act: value, first-order gradients
+    (fused pass) and the R1-style second order (tensor-op form under create_graph)."""
+    from gan_track_b200.torch_utils.ops import rgb
+    torch.manual_seed(C)
+    N, H, W = 3, 37, 41
+    x0 = torch.randn(N, 1, H, W, device=DEV).to(dtype)
+    w0 = (torch.randn(C, 1, 1, 1, device=DEV) * 1.3).to(dtype)
+    b0 = torch.randn(C, device=DEV).to(dtype)
+    dy = torch.randn(N, C, H, W, device=DEV).to(dtype)
+    tol = 2e-3 if dtype == torch.float16 else 2e-5
+    outs = []
+    for ours in (True, False):
+        x, w, b = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        if ours:
+            assert rgb.applicable(x, C)
+            y = rgb.fromrgb1(x, w.reshape(-1), b, act=act, clamp=clamp)
+            assert y.stride(1) == 1 or C == 1
+        else:
+            y = bias_act.bias_act(torch.nn.functional.conv2d(x, w), b, act=act, clamp=clamp)
+        g = torch.autograd.grad(y, [x, w, b], dy, retain_graph=True)                       # fused first-order pass
+        gx, = torch.autograd.grad(y, [x], dy, create_graph=True)                           # R1: gradient w.r.t. the image ...
+        g2 = torch.autograd.grad(gx.float().square().sum(), [w], allow_unused=True)        # ... differentiated w.r.t. the weights
+        outs.append([y.detach()] + [t_.detach().reshape(-1) for t_ in g] + [gx.detach().reshape(-1)] + [t_.detach().reshape(-1) for t_ in g2 if t_ is not None])
+    assert len(outs[0]) == len(outs[1])
+    for a, c in zip(outs[0], outs[1]):
+        assert a.shape == c.shape
+        assert_close(a.float(), c.float().cpu(), tol if a.numel() > C else 10 * tol, 'fromrgb1')
