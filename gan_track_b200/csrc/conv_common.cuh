@@ -38,26 +38,30 @@ struct ConvParams {
     int halo_w, halo_h;                                      // TMA box extent in pixels
 };
 
+// Kernel flavours (compile-time, so that the plain fp16 path carries none of the others' code or registers):
+enum { CONV_F16 = 0, CONV_TF32 = 1, CONV_F16_EP = 2 };
+__host__ __device__ inline int conv_mode(const ConvParams& p) { return p.tf32 ? CONV_TF32 : (p.ep_act != 0 ? CONV_F16_EP : CONV_F16); }
+
 // 32 consecutive accumulator columns (output channels co0 .. co0+31) of one output pixel -> global memory
-// (fp16: 64 bytes, fp32: 128 bytes), through the optional bias + activation epilogue
+// (fp16: 64 bytes, fp32: 128 bytes); CONV_F16_EP runs the bias + activation epilogue on the way
+template <int MODE>
 __device__ __forceinline__ void conv_store32(const ConvParams& p, long long elem_off, int co0, const uint32_t (&r)[32]) {
-    if (p.tf32) {
+    if (MODE == CONV_TF32) {
         float* yp = (float*)p.y + elem_off;
 #pragma unroll
         for (int v = 0; v < 8; v++) *reinterpret_cast<uint4*>(yp + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
         return;
     }
     __half* yp = (__half*)p.y + elem_off;
-    const bool ep = p.ep_act != 0;
-    const hot::Params hp = hot::make_params(p.ep_alpha, p.ep_gain, p.ep_clamp);
-    const bool clamp_on = p.ep_clamp >= 0.f;
 #pragma unroll
     for (int v = 0; v < 4; v++) {
         __half2 h[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(__uint_as_float(r[v * 8 + 2 * k]), __uint_as_float(r[v * 8 + 2 * k + 1]));
-        if (ep) {
+        if (MODE == CONV_F16_EP) {
             // the reference materialises the convolution output in fp16 before bias_act reads it back: round first
+            const hot::Params hp = hot::make_params(p.ep_alpha, p.ep_gain, p.ep_clamp);
+            const bool clamp_on = p.ep_clamp >= 0.f;
             Vec16<__half> bv;
             if (p.ep_bias) bv = ld16(p.ep_bias + co0 + v * 8);
 #pragma unroll

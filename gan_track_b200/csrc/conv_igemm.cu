@@ -53,7 +53,7 @@ struct SmemLayout {
     static constexpr uint32_t TOTAL = TILES + BARS + 1024;   // + slack for the manual 1024-byte alignment
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                               const ConvParams p) {
     typedef SmemLayout<BN, STAGES> L;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kel = p.tf32 ? 32 : BK;           // channels per 128-byte k-chunk
+    constexpr int kel = MODE == CONV_TF32 ? 32 : BK;           // channels per 128-byte k-chunk
     const int kchunks = p.Cin / kel;
     const int nkb = ph.ntaps * kchunks;
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(BM, BN, 0, 0, 0), idesc_tf32 = umma_idesc(BM, BN, 2, 0, 0);
-            const bool tf32 = p.tf32 != 0;
+            constexpr bool tf32 = MODE == CONV_TF32;
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; kb++) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
             tmem_ld_wait();
-            if (valid) conv_store32(p, yoff + c * 32, nt * BN + c * 32, r);
+            if (valid) conv_store32<MODE>(p, yoff + c * 32, nt * BN + c * 32, r);
         }
     }
     tc_fence_before();
@@ -202,22 +202,31 @@ int next_pow2_log2(int v) {
     return l;
 }
 
-template <int BN, int STAGES>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+template <int BN, int STAGES, int MODE>
+int launch_conv_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
     typedef SmemLayout<BN, STAGES> L;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
         if (e != cudaSuccess) {
-            gt_set_error("gt_conv2d_igemm_f16: cannot reserve %u bytes of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
+            gt_set_error("gt_conv2d_igemm: cannot reserve %u bytes of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
             return GT_ERR_CUDA;
         }
         configured = true;
     }
     dim3 grid((unsigned)(p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_n), 1, (unsigned)p.nphases);
-    conv_igemm_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p);
-    GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm_f16");
+    conv_igemm_kernel<BN, STAGES, MODE><<<grid, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm");
     return GT_OK;
+}
+
+template <int BN, int STAGES>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+    switch (conv_mode(p)) {
+        case CONV_TF32: return launch_conv_m<BN, STAGES, CONV_TF32>(tmA, tmB, p, stream);
+        case CONV_F16_EP: return launch_conv_m<BN, STAGES, CONV_F16_EP>(tmA, tmB, p, stream);
+        default: return launch_conv_m<BN, STAGES, CONV_F16>(tmA, tmB, p, stream);
+    }
 }
 
 }  // namespace

@@ -56,7 +56,7 @@ __device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int t
     return it;
 }
 
-template <int BN, int MT, int SB, int NBUF>
+template <int BN, int MT, int SB, int NBUF, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                        const ConvParams p, const int total_items) {
     typedef HaloSmem<BN, MT, SB, NBUF> L;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kel = p.tf32 ? 32 : 64;           // channels per 128-byte chunk
+    constexpr int kel = MODE == CONV_TF32 ? 32 : 64;           // channels per 128-byte chunk
     const int kchunks = p.Cin / kel;
     const uint32_t a_bytes = (uint32_t)(p.halo_w * p.halo_h) * 128u;
     const uint32_t row_pitch = (uint32_t)p.halo_w * 128u;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0, 0), idesc_tf32 = umma_idesc(128, BN, 2, 0, 0);
-            const bool tf32 = p.tf32 != 0;
+            constexpr bool tf32 = MODE == CONV_TF32;
             uint32_t a_it = 0, b_it = 0, t_it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const Item it = decode_item(p, item, TILE_W);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c * 32), r);
                     tmem_ld_wait();
-                    if (valid) conv_store32(p, yoff + c * 32, it.nt * BN + c * 32, r);
+                    if (valid) conv_store32<MODE>(p, yoff + c * 32, it.nt * BN + c * 32, r);
                 }
             }
             tc_fence_before();
@@ -222,23 +222,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
     }
 }
 
-template <int BN, int MT, int SB, int NBUF>
-int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
+template <int BN, int MT, int SB, int NBUF, int MODE>
+int launch_halo_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
     typedef HaloSmem<BN, MT, SB, NBUF> L;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_halo_kernel<BN, MT, SB, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_halo_kernel<BN, MT, SB, NBUF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
         if (e != cudaSuccess) {
-            gt_set_error("gt_conv2d_igemm_f16 (halo): cannot reserve %u bytes of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
+            gt_set_error("gt_conv2d_igemm (halo): cannot reserve %u bytes of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
             return GT_ERR_CUDA;
         }
         configured = true;
     }
     int grid = gt_num_sms();
     if (grid > total_items) grid = total_items;
-    conv_igemm_halo_kernel<BN, MT, SB, NBUF><<<grid, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
-    GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm_f16 (halo)");
+    conv_igemm_halo_kernel<BN, MT, SB, NBUF, MODE><<<grid, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
+    GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm (halo)");
     return GT_OK;
+}
+
+template <int BN, int MT, int SB, int NBUF>
+int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
+    switch (conv_mode(p)) {
+        case CONV_TF32: return launch_halo_m<BN, MT, SB, NBUF, CONV_TF32>(tmA, tmB, p, total_items, stream);
+        case CONV_F16_EP: return launch_halo_m<BN, MT, SB, NBUF, CONV_F16_EP>(tmA, tmB, p, total_items, stream);
+        default: return launch_halo_m<BN, MT, SB, NBUF, CONV_F16>(tmA, tmB, p, total_items, stream);
+    }
 }
 
 }  // namespace
