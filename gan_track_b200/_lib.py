@@ -45,6 +45,9 @@ _PROTOTYPES = {
     'gt_fromrgb1_bwd_workspace': (_ll, [_i]),
     'gt_fromrgb1_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _ll, _i, _vp]),
     'gt_fromrgb1_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _ll, _i, _vp]),
+    'gt_torgb1_bwd_workspace': (_ll, [_i, _i]),
+    'gt_torgb1_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _ll, _i, _vp]),
+    'gt_torgb1_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _i, _vp]),
     'gt_conv_igemm_config': (_i, [_i]),
     'gt_conv_wgrad_config': (_i, [_i]),
     'gt_conv_pack_weight_f16': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),

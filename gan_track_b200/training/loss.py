@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from ..torch_utils import training_stats
-from ..torch_utils.ops import conv2d_gradfix, upfirdn2d
+from ..torch_utils.ops import conv2d_gradfix, rgb, upfirdn2d
 
 
 class Loss:
@@ -79,7 +79,8 @@ class StyleGAN2Loss(Loss):
     def _g_pathlen(self, gen_z, gen_c, gain):
         """Path-length regulariser on a shrunken batch: second-order backward through the synthesis network."""
         n = gen_z.shape[0] // self.pl_batch_shrink
-        fake, ws = self.run_G(gen_z[:n], gen_c[:n])
+        with rgb.op_by_op_torgb():          # this pass differentiates G's backward: keep ToRGB in its differentiable op-by-op form
+            fake, ws = self.run_G(gen_z[:n], gen_c[:n])
         probe = torch.randn_like(fake) / np.sqrt(fake.shape[2] * fake.shape[3])
         with conv2d_gradfix.no_weight_gradients(self.pl_no_weight_grad):
             jac, = torch.autograd.grad(outputs=[(fake * probe).sum()], inputs=[ws], create_graph=True, only_inputs=True)

@@ -282,6 +282,9 @@ class ToRGBLayer(torch.nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
+        if (not fused_modconv) and self.weight.shape[2] == 1 and rgb.torgb_applicable(x, self.out_channels):
+            # single-channel slices: modulation + 1x1 convolution + bias + clamp in one pass over x (csrc/rgb.cu)
+            return rgb.torgb1(x, self.weight, styles, self.bias, clamp=self.conv_clamp)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
 

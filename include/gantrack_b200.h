@@ -171,6 +171,18 @@ int gt_fromrgb1_bwd(const void* dy, const void* y, const void* x, const void* w,
                     long long workspace_floats, int dtype, int act, float alpha, float gain, float clamp, long long NP, int C,
                     void* stream);
 
+/* ---- ToRGB with ONE image channel --------------------------------------------------------------------------------------
+ * ToRGBLayer.forward (S3/training/networks_stylegan2.py:338-358) = modulated 1x1 convolution without demodulation + linear
+ * bias_act with clamp, as one pass over x:  y[n,p] = clamp(round_T(sum_c round_T(x[n,p,c] s[n,c]) w[c]) + b).
+ * x / dx: [N,P,C] T channels-last, s / ds: [N,C] fp32, w: [C] T, b: [1] T or NULL, y / dy: [N,P] T; C/vec a power of two <= 32.
+ * gt_torgb1_bwd: dx, ds[n,c] = sum_p (dy w[c]) x, dw[c] = sum_{n,p} dy round_T(x s), db = sum dy (all fp32 sums, fixed order);
+ * workspace: gt_torgb1_bwd_workspace(N, C) floats. */
+long long gt_torgb1_bwd_workspace(int N, int C);
+int gt_torgb1_fwd(const void* x, const float* s, const void* w, const void* b, void* y, int dtype, float clamp, int N, long long P, int C,
+                  void* stream);
+int gt_torgb1_bwd(const void* dy, const void* x, const float* s, const void* w, void* dx, float* ds, float* dw, float* db,
+                  float* workspace, long long workspace_floats, int dtype, int N, long long P, int C, void* stream);
+
 /* ---- ADA geometric warp (fp32) ------------------------------------------------------------------------------------
  * Replaces the op sequence of S3/training/augment_mi.py:303-318: F.pad(reflect, margins) -> upfirdn2d.upsample2d(taps,
  * up=2) -> F.grid_sample(F.affine_grid(theta, [B,C,OH,OW]), bilinear, zeros, align_corners=False).  `margins` is a DEVICE

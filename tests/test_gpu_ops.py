@@ -438,3 +438,34 @@ def test_fromrgb1_matches_conv_bias_act(dtype, C, act, clamp):
     for a, c in zip(outs[0], outs[1]):
         assert a.shape == c.shape
         assert_close(a.float(), c.float().cpu(), tol if a.numel() > C else 10 * tol, 'fromrgb1')
+
+
+@pytest.mark.parametrize('dtype,C,clamp', [(torch.float16, 64, 256.0), (torch.float16, 128, 0.3), (torch.float32, 32, None), (torch.float16, 256, 256.0)])
+def test_torgb1_matches_modulated_conv_bias_act(dtype, C, clamp):
+    """csrc/rgb.cu (ToRGB with one image channel) against the op-by-op form (modulate, 1x1 convolution, bias_act): value, the
+    first-order gradients of x / weight / styles / bias (fused pass) and a path-length-style second order (under create_graph)."""
+    from gan_track_b200.torch_utils.ops import rgb
+    torch.manual_seed(C)
+    N, H, W = 3, 24, 40
+    x0 = torch.randn(N, C, H, W, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    w0 = torch.randn(1, C, 1, 1, device=DEV) / np.sqrt(C)
+    s0 = torch.randn(N, C, device=DEV) * 0.5 + 1
+    b0 = torch.randn(1, device=DEV) * 0.1
+    dy = torch.randn(N, 1, H, W, device=DEV).to(dtype)
+    tol = 4e-3 if dtype == torch.float16 else 2e-5
+    outs = []
+    for ours in (True, False):
+        x, w, s, b = (t_.clone().requires_grad_(True) for t_ in (x0, w0, s0, b0))
+        if ours:
+            assert rgb.torgb_applicable(x, 1)
+            y = rgb.torgb1(x, w, s, b, clamp=clamp)
+        else:
+            y = rgb._torgb_reference(x, w, s, b, clamp)
+        g = torch.autograd.grad(y, [x, w, s, b], dy, retain_graph=True)
+        gs, = torch.autograd.grad(y, [s], dy, create_graph=True)                   # path length: gradient w.r.t. the styles ...
+        g2 = torch.autograd.grad(gs.square().sum(), [w, x], allow_unused=True)      # ... differentiated w.r.t. weight and x
+        outs.append([y.detach()] + [t_.detach() for t_ in g] + [gs.detach()] + [t_.detach() for t_ in g2 if t_ is not None])
+    assert len(outs[0]) == len(outs[1])
+    for i, (a, c) in enumerate(zip(outs[0], outs[1])):
+        assert a.shape == c.shape
+        assert_close(a.float(), c.float().cpu(), tol if i != 4 else 10 * tol, f'torgb1 output {i}')
