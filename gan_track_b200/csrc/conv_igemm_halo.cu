@@ -252,6 +252,10 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
 
 }  // namespace
 
+bool gt_conv_halo2_applicable(const ConvParams& p, int maxOH, int maxOW);
+int gt_launch_conv_halo2(const void* x, long long xs_n, long long xs_h, long long xs_w, int H, int W, const void* wpacked, int ntaps_total, ConvParams& p,
+                         int ext_x, int ext_y, int maxOH, int maxOW, cudaStream_t stream);
+
 int g_conv_halo_tuning = 0;   // 0: Cout%256 -> BN 256 x 2 sub-tiles, one accumulator set; 2: BN 256 x 1 sub-tile, two sets; 3: BN 128 everywhere
 
 static void pick_tile(int Cout, int Cin, int& BN, int& MT) {
@@ -299,6 +303,8 @@ int gt_launch_conv_halo(const void* x, long long xs_n, long long xs_h, long long
         maxOW = ph.OWp > maxOW ? ph.OWp : maxOW;
     }
     GT_REQUIRE(ext_x <= 2 && ext_y <= 2, "gt_conv2d_igemm_f16 (halo): tap extent %dx%d exceeds the staged halo", ext_x, ext_y);
+    if (g_conv_halo_tuning == 5 && gt_conv_halo2_applicable(p, maxOH, maxOW))      // CTA-pair kernel (conv_igemm_halo2.cu)
+        return gt_launch_conv_halo2(x, xs_n, xs_h, xs_w, H, W, wpacked, ntaps_total, p, ext_x, ext_y, maxOH, maxOW, stream);
     p.halo_w = SUB_W * MT + ext_x;
     p.halo_h = SUB_H + ext_y;
     p.n_tiles = p.Cout / BN;
