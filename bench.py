@@ -252,6 +252,14 @@ def hot_kernel_rooflines(device, pk):
     ms = timeit([lambda x=x: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4) for x in xs])
     add('upfirdn2d 4x4 blur [32,64,257,257]->[32,64,256,256] f16 NHWC', 'upfirdn2d_tma_kernel<half>', 'hbm', (32 * 64 * 257 * 257 + 32 * 64 * 256 * 256) * 2, ms)
     del xs
+    xs = rot(lambda: t16([32, 64, 256, 256]), 32 * 64 * 256 * 256 * 2 * 5 // 4)
+    ms = timeit([lambda x=x: upfirdn2d.upfirdn2d(x, f, down=2, padding=[1, 1, 1, 1]) for x in xs])
+    add('upfirdn2d 4x4 down=2 [32,64,256,256]->[32,64,128,128] f16 NHWC', 'upfirdn2d_tma_down2_kernel<half>', 'hbm', 32 * 64 * (256 * 256 + 128 * 128) * 2, ms)
+    del xs
+    xs = rot(lambda: t16([32, 64, 128, 128]), 32 * 64 * 128 * 128 * 2 * 5)
+    ms = timeit([lambda x=x: upfirdn2d.upfirdn2d(x, f, up=2, padding=[2, 1, 2, 1], gain=4) for x in xs])
+    add('upfirdn2d 4x4 up=2 [32,64,128,128]->[32,64,256,256] f16 NHWC', 'upfirdn2d_tma_up2_kernel<half,0,0>', 'hbm', 32 * 64 * (256 * 256 + 128 * 128) * 2, ms)
+    del xs
 
     shape = [32, 64, 256, 256]
     nb = 32 * 64 * 256 * 256 * 2

@@ -33,6 +33,7 @@ struct ConvParams {
     const __half* ep_bias;
     int ep_act;
     float ep_alpha, ep_gain, ep_clamp;
+    int dbg_no_store;                // experiments only: run the whole pipeline but skip the global stores
     // halo kernel only
     int dy_min[CONV_MAX_PHASES], dx_min[CONV_MAX_PHASES];   // most negative tap offset of the phase = halo origin
     int halo_w, halo_h;                                      // TMA box extent in pixels

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
 #pragma unroll 1
             for (int j = 0; j < MT; j++) {
                 const int b = it.ox0 + j * SUB_W + lw;
-                const bool valid = (a < ph.OHp) && (b < ph.OWp);
+                const bool valid = (a < ph.OHp) && (b < ph.OWp) && !p.dbg_no_store;
                 const long long yoff = (long long)it.n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
                                        (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN;
 #pragma unroll 1
@@ -302,6 +302,7 @@ int gt_launch_conv_halo(const void* x, long long xs_n, long long xs_h, long long
         maxOH = ph.OHp > maxOH ? ph.OHp : maxOH;
         maxOW = ph.OWp > maxOW ? ph.OWp : maxOW;
     }
+    p.dbg_no_store = (g_conv_halo_tuning == 6);
     GT_REQUIRE(ext_x <= 2 && ext_y <= 2, "gt_conv2d_igemm_f16 (halo): tap extent %dx%d exceeds the staged halo", ext_x, ext_y);
     if (g_conv_halo_tuning == 5 && gt_conv_halo2_applicable(p, maxOH, maxOW))      // CTA-pair kernel (conv_igemm_halo2.cu)
         return gt_launch_conv_halo2(x, xs_n, xs_h, xs_w, H, W, wpacked, ntaps_total, p, ext_x, ext_y, maxOH, maxOW, stream);

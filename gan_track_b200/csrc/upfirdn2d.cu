@@ -18,6 +18,9 @@
 int gt_upfirdn2d_try_tma(const void* x, const float* f, long long fs_h, long long fs_w, int flip, float gain, void* y, int dtype, int N, int C, int H, int W,
                          long long xs_n, long long xs_h, long long xs_w, int OH, int OW, long long ys_n, long long ys_h, long long ys_w, int padx0, int pady0,
                          cudaStream_t st);
+int gt_upfirdn2d_try_tma_strided(const void* x, const float* f, long long fs_h, long long fs_w, int flip, float gain, void* y, int dtype, int N, int C, int H, int W,
+                                 long long xs_n, long long xs_h, long long xs_w, int OH, int OW, long long ys_n, long long ys_h, long long ys_w, int up, int down, int padx0,
+                                 int pady0, cudaStream_t st);
 
 namespace {
 
@@ -478,6 +481,12 @@ extern "C" int gt_upfirdn2d(const void* x, const float* f, void* y, int dtype, i
         (long long)N * OH * OW * C >= (1 << 20)) {
         // the blur around the resampling convolutions on channels-last tensors: TMA-staged kernel (upfirdn2d_tma.cu)
         const int rc = gt_upfirdn2d_try_tma(x, f, fs_h, fs_w, flip ? 1 : 0, gain, y, dtype, N, C, H, W, xs_n, xs_h, xs_w, OH, OW, ys_n, ys_h, ys_w, padx0, pady0, st);
+        if (rc >= 0) return rc;
+    }
+    if (upx == upy && downx == downy && ((upx == 2 && downx == 1) || (upx == 1 && downx == 2)) && fh == 4 && fw == 4 && xs_c == 1 && ys_c == 1 &&
+        (dtype == GT_F16 || dtype == GT_F32) && (long long)N * C * (upx == 2 ? (long long)OH * OW : (long long)H * W) >= (1 << 20) && gt_stream_variant() == 0) {
+        // factor-2 resampling of the skip branches on channels-last tensors (upfirdn2d_tma_strided.cu)
+        const int rc = gt_upfirdn2d_try_tma_strided(x, f, fs_h, fs_w, flip ? 1 : 0, gain, y, dtype, N, C, H, W, xs_n, xs_h, xs_w, OH, OW, ys_n, ys_h, ys_w, upx, downx, padx0, pady0, st);
         if (rc >= 0) return rc;
     }
     switch (dtype) {

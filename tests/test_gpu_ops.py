@@ -268,6 +268,72 @@ def test_upfirdn2d_full_size_vs_depthwise_conv(N, C, H, cl):
     assert_close(y2.float() * 2, y.float(), 2e-3, 'linearity')
 
 
+STRIDED_TMA_CASES = [
+    # (up, down, padding, N, C, H, W)
+    (2, 1, [2, 1, 2, 1], 2, 64, 96, 96),      # backward of the skip downsample / upsample2d
+    (2, 1, [1, 2, 1, 2], 2, 64, 67, 45),      # odd parity, ragged tiles
+    (2, 1, [3, 0, 2, 1], 1, 128, 50, 41),     # mixed parity
+    (2, 1, [0, 0, 0, 0], 2, 64, 64, 80),
+    (2, 1, [-1, 2, 1, -2], 2, 64, 72, 64),    # cropping
+    (1, 2, [1, 1, 1, 1], 2, 64, 128, 128),    # the skip downsample (OPS/conv2d_resample.py:94-97)
+    (1, 2, [2, 2, 2, 2], 2, 64, 131, 97),
+    (1, 2, [0, 1, 3, 0], 1, 128, 100, 90),
+    (1, 2, [-1, 1, 2, -1], 2, 64, 96, 130),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+@pytest.mark.parametrize('flip', [False, True])
+@pytest.mark.parametrize('case', STRIDED_TMA_CASES, ids=lambda c: f'up{c[0]}down{c[1]}pad{"_".join(map(str, c[2]))}')
+def test_upfirdn2d_strided_tma_vs_oracle(case, flip, dtype):
+    """Factor-2 resampling on channels-last tensors large enough for the TMA-staged kernels (upfirdn2d_tma_strided.cu),
+    with an asymmetric 4x4 filter so that tap orientation, flip and the phase/tap pairing are all pinned by the oracle."""
+    up, down, padding, N, C, H, W = case
+    if dtype == torch.float32:
+        C //= 2 if C > 64 else 1
+    torch.manual_seed(3)
+    x = torch.randn(N, C, H, W, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    f = torch.randn(4, 4, device=DEV)
+    kw = dict(up=up, down=down, padding=padding, flip_filter=flip, gain=1.7)
+    y = upfirdn2d.upfirdn2d(x, f, **kw)
+    yo = R.upfirdn2d(x.detach().float().cpu(), f.cpu(), **kw)
+    assert y.shape == yo.shape
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert_close(y, yo, TOL[dtype], 'y')
+    dy = torch.randn_like(y)
+    dx, = torch.autograd.grad(y, x, dy)          # the other strided kernel
+    xo = x.detach().float().cpu().requires_grad_(True)
+    dxo, = torch.autograd.grad(R.upfirdn2d(xo, f.cpu(), **kw), xo, dy.float().cpu())
+    assert_close(dx, dxo, TOL[dtype], 'dx')
+
+
+@pytest.mark.parametrize('up,down,shape', [(1, 2, (32, 64, 256, 256)), (2, 1, (32, 64, 128, 128)), (1, 2, (32, 512, 32, 32)), (2, 1, (16, 256, 32, 32))])
+def test_upfirdn2d_strided_tma_equals_direct_full_size(up, down, shape):
+    """BASELINE.json sizes: TMA-staged vs the thread-per-output kernel (an independent code path) + adjointness
+    <upfirdn(x), dy> == <x, upfirdn_backward(dy)>."""
+    from gan_track_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(4)
+    x = torch.randn(shape, device=DEV, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    f4 = upfirdn2d.setup_filter(gg.F4, device=DEV)
+    kw = dict(up=up, down=down, padding=[2, 1, 2, 1] if up == 2 else [1, 1, 1, 1], gain=up * up)
+    out = []
+    for variant in (0, 1):
+        old = lib.gt_stream_config(variant)
+        try:
+            out.append(upfirdn2d.upfirdn2d(x, f4, **kw))
+        finally:
+            lib.gt_stream_config(old)
+    assert_close(out[0], out[1], 1e-3, 'tma vs direct')
+    xr = x.clone().requires_grad_(True)
+    y = upfirdn2d.upfirdn2d(xr, f4, **kw)
+    dy = torch.randn_like(y)
+    dx, = torch.autograd.grad(y, xr, dy)
+    lhs = (y.detach().double() * dy.double()).sum()
+    rhs = (x.double() * dx.double()).sum()
+    assert abs(lhs - rhs) <= 1e-2 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+
+
 # ---------------------------------------------------------------------------------------------------- conv family
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16])

@@ -40,6 +40,9 @@ for name, shape, dt, cl, kw in [
     ('blur after up-conv  [32,512,33,33] f16 NHWC', (32, 512, 33, 33), torch.float16, True, dict(padding=[1, 1, 1, 1], gain=4)),
     ('blur before down-conv [32,64,256,256] f16 NHWC', (32, 64, 256, 256), torch.float16, True, dict(padding=[2, 2, 2, 2])),
     ('skip downsample     [32,64,256,256] f16 NHWC', (32, 64, 256, 256), torch.float16, True, dict(down=2, padding=[1, 1, 1, 1])),
+    ('skip downsample     [32,256,64,64] f16 NHWC', (32, 256, 64, 64), torch.float16, True, dict(down=2, padding=[1, 1, 1, 1])),
+    ('skip downsample bwd [32,64,128,128] f16 NHWC', (32, 64, 128, 128), torch.float16, True, dict(up=2, padding=[2, 1, 2, 1], gain=4)),
+    ('skip downsample bwd [32,256,32,32] f16 NHWC', (32, 256, 32, 32), torch.float16, True, dict(up=2, padding=[2, 1, 2, 1], gain=4)),
     ('blur fp32 planes    [32,512,33,33] f32 NCHW', (32, 512, 33, 33), torch.float32, False, dict(padding=[1, 1, 1, 1], gain=4)),
     ('blur fp32 planes    [32,512,17,17] f32 NCHW', (32, 512, 17, 17), torch.float32, False, dict(padding=[1, 1, 1, 1], gain=4)),
     ('img upsample        [32,1,128,128] f32 NCHW', (32, 1, 128, 128), torch.float32, False, dict(up=2, padding=[2, 1, 2, 1], gain=4)),
