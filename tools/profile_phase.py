@@ -28,6 +28,6 @@ rows = sorted([r for r in prof.key_averages() if r.device_time_total > 0], key=l
 total = sum(r.device_time_total for r in rows)
 with open(out, 'w') as f:
     f.write(f'phase {name}: gpu busy {total / 1e3:.2f} ms, kernels {sum(r.count for r in rows)}\n')
-    for r in rows[:70]:
+    for r in rows[:int(os.environ.get("GT_PROFILE_ROWS", "70"))]:
         f.write(f'{r.device_time_total / total * 100:6.2f} {r.device_time_total / 1e3:9.3f} ms {r.count:6d} x {r.device_time_total / max(r.count, 1):9.1f} us  {r.key[:140]}\n')
 print(open(out).read())
