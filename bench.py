@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-overlap', action='store_true')
+    ap.add_argument('--two-pass-dmain', action='store_true', help='score generated and real images in two discriminator passes (the reference schedule) instead of one merged pass')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying per-phase CUDA graphs')
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--profile-range', action='store_true', help='cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)')
@@ -322,7 +323,7 @@ def run_ours(args):
     global_batch = batch_gpu * world
     gamma = 0.0002 * res ** 2 / global_batch if res != 256 or global_batch != 32 else 0.4096
     cfg = tl.claro_config(resolution=res, batch=global_batch, num_gpus=world, cbase=cbase, aug=args.aug, gamma=gamma)
-    trainer = tl.Trainer(cfg, rank=rank, device=device, overlap=not args.no_overlap, use_graphs=not args.no_graphs)
+    trainer = tl.Trainer(cfg, rank=rank, device=device, overlap=not args.no_overlap, use_graphs=not args.no_graphs, merge_d_passes=not args.two_pass_dmain)
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_img = (torch.rand([batch_gpu, 1, res, res], generator=g) * 255).pin_memory()
@@ -417,7 +418,7 @@ def run_ours(args):
                                    f'lazy R1 (every 16) + path-length (every 4), ADA={args.aug}', 'global_batch': global_batch, 'batch_gpu': batch_gpu,
                        'parallelism': f'dp{world}', 'phase_counts_in_timed_region': phase_counts,
                        'l2_policy': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush in the step loop',
-                       'conv_routes': conv_stats, 'cuda_graphs': not args.no_graphs, 'phase_ms': phase_ms},
+                       'conv_routes': conv_stats, 'cuda_graphs': not args.no_graphs, 'dmain_one_pass': not args.two_pass_dmain, 'phase_ms': phase_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base, 'roofline_all': roof_all,
         }
         if flops_per_img:

@@ -24,7 +24,8 @@ class Loss:
 
 class StyleGAN2Loss(Loss):
     def __init__(self, device, G, D, augment_pipe=None, r1_gamma=10, style_mixing_prob=0, pl_weight=0, pl_batch_shrink=2,
-                 pl_decay=0.01, pl_no_weight_grad=False, blur_init_sigma=0, blur_fade_kimg=0, allow_aug_debug_print=False):
+                 pl_decay=0.01, pl_no_weight_grad=False, blur_init_sigma=0, blur_fade_kimg=0, allow_aug_debug_print=False,
+                 merge_d_passes=False):
         super().__init__()
         self.device = device
         self.G = G
@@ -40,6 +41,10 @@ class StyleGAN2Loss(Loss):
         self.blur_init_sigma = blur_init_sigma
         self.blur_fade_kimg = blur_fade_kimg
         self.allow_aug_debug_print = allow_aug_debug_print   # accepted for interface parity; debug plotting is not part of the path
+        # Dmain scores the generated and the real batch with the same D; with merge_d_passes the two forward / backward
+        # passes of the reference (S3/training/loss.py:102-139) run as one pass over the concatenated batch (same sums, see
+        # _d_main_merged); off by default = the reference's schedule
+        self.merge_d_passes = merge_d_passes
 
     def run_G(self, z, c, update_emas=False):
         ws = self.G.mapping(z, c, update_emas=update_emas)
@@ -55,14 +60,17 @@ class StyleGAN2Loss(Loss):
         img = self.G.synthesis(ws, update_emas=update_emas)
         return img, ws
 
-    def run_D(self, img, c, blur_sigma=0, update_emas=False, allow_aug_debug_print=False):
+    def _pre_D(self, img, blur_sigma=0, allow_aug_debug_print=False):
         blur_size = np.floor(blur_sigma * 3)
         if blur_size > 0:
             f = torch.arange(-blur_size, blur_size + 1, device=img.device).div(blur_sigma).square().neg().exp2()
             img = upfirdn2d.filter2d(img, f / f.sum())
         if self.augment_pipe is not None:
             img = self.augment_pipe(img, allow_aug_debug_print)
-        return self.D(img, c, update_emas=update_emas)
+        return img
+
+    def run_D(self, img, c, blur_sigma=0, update_emas=False, allow_aug_debug_print=False):
+        return self.D(self._pre_D(img, blur_sigma, allow_aug_debug_print), c, update_emas=update_emas)
 
     # -- the four sub-graphs ------------------------------------------------------------------------------------
 
@@ -124,6 +132,49 @@ class StyleGAN2Loss(Loss):
             total = total + loss_r1
         total.mean().mul(gain).backward()
 
+    def _mbstd_group(self, n):
+        """Group size the discriminator's MinibatchStdLayer uses for a batch of n, None if it has no such layer."""
+        layer = getattr(getattr(self.D, 'b4', None), 'mbstd', None)
+        if layer is None:
+            return 1
+        if layer.group_size is None:
+            return None             # one group = the whole batch: merging would change the statistics
+        return min(int(layer.group_size), int(n))
+
+    def _can_merge_d(self, real_img, gen_z):
+        if not self.merge_d_passes or real_img.shape[0] != gen_z.shape[0]:
+            return False
+        g = self._mbstd_group(gen_z.shape[0])
+        return g is not None and gen_z.shape[0] % g == 0
+
+    def _d_main_merged(self, real_img, real_c, gen_z, gen_c, gain, blur_sigma):
+        """Dmain as ONE discriminator pass over [generated, real]: loss = mean softplus(D(fake)) + mean softplus(-D(real)),
+        one backward.  Per-sample work in D is independent of the batch except MinibatchStdLayer, whose group j is the samples
+        {j, j + n, j + 2n, ...} (n = batch / G, networks_stylegan2.py:650-665); the two batches are interleaved in chunks of
+        batch/G so that every group of the merged batch is exactly a group of one of the separate passes.  Random draws
+        (G noise, ADA parameters for fake, then for real) happen in the reference's order; parameter gradients are the same
+        sums, accumulated in one pass instead of two."""
+        n = gen_z.shape[0]
+        g = self._mbstd_group(n)
+        fake, _ = self.run_G(gen_z, gen_c, update_emas=True)
+        fake = self._pre_D(fake, blur_sigma)
+        real = self._pre_D(real_img.detach(), blur_sigma, self.allow_aug_debug_print)
+
+        def interleave(a, b):
+            return torch.cat([t for pair in zip(a.chunk(g), b.chunk(g)) for t in pair])
+
+        logits = self.D(interleave(fake, real), interleave(gen_c, real_c), update_emas=True)
+        parts = logits.chunk(2 * g)
+        logits_fake, logits_real = torch.cat(parts[0::2]), torch.cat(parts[1::2])
+        training_stats.report('Loss/scores/fake', logits_fake)
+        training_stats.report('Loss/signs/fake', logits_fake.sign())
+        loss_fake = torch.nn.functional.softplus(logits_fake)
+        training_stats.report('Loss/scores/real', logits_real)
+        training_stats.report('Loss/signs/real', logits_real.sign())
+        loss_real = torch.nn.functional.softplus(-logits_real)
+        training_stats.report('Loss/D/loss', loss_fake + loss_real)
+        (loss_fake.mean() + loss_real.mean()).mul(gain).backward()
+
     def accumulate_gradients(self, phase, real_img, real_c, gen_z, gen_c, gain, cur_nimg):
         assert phase in ['Gmain', 'Greg', 'Gboth', 'Dmain', 'Dreg', 'Dboth']
         if self.pl_weight == 0:
@@ -138,6 +189,9 @@ class StyleGAN2Loss(Loss):
         if phase in ('Greg', 'Gboth'):
             self._g_pathlen(gen_z, gen_c, gain)
         loss_fake = 0
+        if phase == 'Dmain' and self._can_merge_d(real_img, gen_z):
+            self._d_main_merged(real_img, real_c, gen_z, gen_c, gain, blur_sigma)
+            return
         if phase in ('Dmain', 'Dboth'):
             loss_fake = self._d_fake(gen_z, gen_c, gain, blur_sigma)
         if phase in ('Dmain', 'Dreg', 'Dboth'):

@@ -184,7 +184,7 @@ class GradBucketReducer:
 
 
 class Trainer:
-    def __init__(self, cfg, rank=0, device=None, overlap=True, ops_sanity=True, use_graphs=False):
+    def __init__(self, cfg, rank=0, device=None, overlap=True, ops_sanity=True, use_graphs=False, merge_d_passes=None):
         self.cfg = cfg
         self.rank = rank
         self.num_gpus = cfg.num_gpus
@@ -215,6 +215,8 @@ class Trainer:
                     for t in misc.params_and_buffers(module):
                         torch.distributed.broadcast(t, src=0)
         self.loss = loss_mod.StyleGAN2Loss(device=dev, G=self.G, D=self.D, augment_pipe=self.augment_pipe, **cfg.loss_kwargs)
+        # Dmain as one discriminator pass over [generated, real] (loss.StyleGAN2Loss._d_main_merged): on by default on the GPU
+        self.loss.merge_d_passes = (self.device.type == 'cuda') if merge_d_passes is None else bool(merge_d_passes)
 
         # Graph mode: parameters live in flat buffers; gradient scrub + Adam and the G_ema lerp are single kernels (csrc/optim.cu)
         self.flat = None

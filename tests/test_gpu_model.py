@@ -166,3 +166,28 @@ def test_trainer_cuda_graph_mode_runs_and_captures():
     assert moved > 0
     for p in trainer.D.parameters():
         assert torch.isfinite(p).all()
+
+
+@pytest.mark.parametrize('fp32,tol', [(True, 2e-5), (False, 2e-2)])
+def test_dmain_merged_pass_equals_two_passes_cuda(fp32, tol):
+    """Dmain as one discriminator pass over the interleaved [generated, real] batch vs the reference's two passes, on the
+    CUDA kernels (fp32 model and fp16 model on the tcgen05 path): same parameter gradients up to summation order."""
+    from gan_track_b200.training import training_loop as tl
+    grads = []
+    for merge in (False, True):
+        cfg = tl.claro_config(resolution=64, batch=16, num_gpus=1, cbase=4096, cmax=64, map_depth=2, fp32=fp32)
+        tr = tl.Trainer(cfg, rank=0, device='cuda', use_graphs=False, merge_d_passes=merge)
+        tr.augment_pipe.p.fill_(0.6)
+        g = torch.Generator().manual_seed(3)
+        real = (torch.rand([16, 1, 64, 64], generator=g) * 2 - 1).cuda()
+        c = torch.nn.functional.one_hot(torch.randint(0, 2, [16], generator=g), 2).float().cuda()
+        z = torch.randn([16, 512], generator=g).cuda()
+        tr.D.requires_grad_(True)
+        tr.G.requires_grad_(False)
+        torch.manual_seed(9)
+        tr.loss.accumulate_gradients(phase='Dmain', real_img=real, real_c=c, gen_z=z, gen_c=c.flip(0), gain=1, cur_nimg=0)
+        grads.append({n: p.grad.detach().clone() for n, p in tr.D.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 10
+    for n in grads[0]:
+        assert torch.isfinite(grads[1][n]).all(), n
+        assert rel_err(grads[1][n], grads[0][n]) <= tol, (n, rel_err(grads[1][n], grads[0][n]))

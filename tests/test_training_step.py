@@ -51,6 +51,47 @@ def test_single_process_step_schedule_and_updates():
     assert float(tr.augment_pipe.p) >= 0
 
 
+def _dmain_grads(merge, batch=8, aug_p=0.7):
+    from gan_track_b200.torch_utils import training_stats
+    with oracle_ops():
+        tr = tl.Trainer(tiny_cfg(batch=batch), rank=0, device='cpu', overlap=False, merge_d_passes=merge)
+        tr.augment_pipe.p.fill_(aug_p)
+        real, c = batch_for(0, batch)
+        g = torch.Generator().manual_seed(11)
+        z = torch.randn([batch, 16], generator=g)
+        gc = torch.nn.functional.one_hot(torch.randint(0, 2, [batch], generator=g), 2).float()
+        tr.D.requires_grad_(True)
+        tr.G.requires_grad_(False)
+        torch.manual_seed(5)
+        table = training_stats._table(torch.device('cpu'))
+        table.zero_()
+        tr.loss.accumulate_gradients(phase='Dmain', real_img=real / 127.5 - 1, real_c=c, gen_z=z, gen_c=gc, gain=1, cur_nimg=0)
+        grads = {n: p.grad.clone() for n, p in tr.D.named_parameters() if p.grad is not None}
+        stats = {k: table[row].clone() for k, row in training_stats._name_to_row.items() if k.startswith('Loss/')}
+    return grads, stats
+
+
+def test_dmain_merged_pass_equals_two_passes():
+    """One discriminator pass over the interleaved [generated, real] batch (MinibatchStd groups preserved, same random
+    draws) gives the parameter gradients and the logged statistics of the reference's two passes."""
+    ga, sa = _dmain_grads(False)
+    gb, sb = _dmain_grads(True)
+    assert ga.keys() == gb.keys() and len(ga) > 10
+    for n in ga:
+        scale = float(ga[n].abs().max().clamp_min(1e-12))
+        assert float((ga[n] - gb[n]).abs().max()) <= 1e-5 * scale + 1e-9, n
+    assert sa.keys() == sb.keys() and {'Loss/scores/fake', 'Loss/scores/real', 'Loss/D/loss'} <= set(sa.keys())
+    for k in sa:
+        assert torch.allclose(sa[k], sb[k], rtol=1e-5, atol=1e-6), k
+    # batches that do not split into whole MinibatchStd groups keep the two-pass schedule
+    with oracle_ops():
+        tr = tl.Trainer(tiny_cfg(batch=4), rank=0, device='cpu', overlap=False, merge_d_passes=True)
+        assert tr.loss._can_merge_d(torch.zeros(4, 1, 16, 16), torch.zeros(4, 16))
+        assert not tr.loss._can_merge_d(torch.zeros(4, 1, 16, 16), torch.zeros(2, 16))
+        tr.D.b4.mbstd.group_size = None
+        assert not tr.loss._can_merge_d(torch.zeros(4, 1, 16, 16), torch.zeros(4, 16))
+
+
 def _worker(rank, world, port, overlap, out_dir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
