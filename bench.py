@@ -288,7 +288,21 @@ def hot_kernel_rooflines(device, pk):
     add('mod_scale fwd [32,64,256,256] f16 NHWC', 'mod_scale_fwd_bulk_kernel<half>', 'hbm', 2 * nb, ms)
     ms = timeit([lambda x=x: modulated.demod_act(x, dm, nz, b, act='lrelu', gain=float(np.sqrt(2)), clamp=256.0) for x in xs])
     add('demod_act fwd [32,64,256,256] f16 NHWC', 'demod_act_fwd_bulk_kernel<half,lrelu>', 'hbm', 2 * nb, ms)
-    del xs
+    # backward passes through autograd on retained graphs (per-sample style / demodulation / noise / bias gradients included)
+    graphs = []
+    for x in xs[:3]:
+        xr, sr = x.detach().requires_grad_(True), sm.clone().requires_grad_(True)
+        graphs.append((modulated.mod_scale(xr, sr), [xr, sr]))
+    dy = torch.randn_like(xs[0])
+    ms = timeit([lambda g=g: torch.autograd.grad(g[0], g[1], dy, retain_graph=True) for g in graphs])
+    add('mod_scale bwd (gx + gs) [32,64,256,256] f16 NHWC', 'mod_scale_bwd_bulk_kernel<half>', 'hbm', 3 * nb, ms)
+    graphs = []
+    for x in xs[:3]:
+        xr, dr, nr, br = x.detach().requires_grad_(True), dm.clone().requires_grad_(True), nz.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        graphs.append((modulated.demod_act(xr, dr, nr, br, act='lrelu', gain=float(np.sqrt(2)), clamp=256.0), [xr, dr, nr, br]))
+    ms = timeit([lambda g=g: torch.autograd.grad(g[0], g[1], dy, retain_graph=True) for g in graphs])
+    add('demod_act bwd (gx + gd + gnoise + gb) [32,64,256,256] f16 NHWC', 'demod_act_bwd_bulk_kernel<half,lrelu>', 'hbm', 4 * nb, ms)
+    del graphs, xs
     return out
 
 

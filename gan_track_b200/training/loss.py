@@ -25,7 +25,7 @@ class Loss:
 class StyleGAN2Loss(Loss):
     def __init__(self, device, G, D, augment_pipe=None, r1_gamma=10, style_mixing_prob=0, pl_weight=0, pl_batch_shrink=2,
                  pl_decay=0.01, pl_no_weight_grad=False, blur_init_sigma=0, blur_fade_kimg=0, allow_aug_debug_print=False,
-                 merge_d_passes=False):
+                 merge_d_passes=False, merge_mapping_passes=False):
         super().__init__()
         self.device = device
         self.G = G
@@ -45,8 +45,22 @@ class StyleGAN2Loss(Loss):
         # passes of the reference (S3/training/loss.py:102-139) run as one pass over the concatenated batch (same sums, see
         # _d_main_merged); off by default = the reference's schedule
         self.merge_d_passes = merge_d_passes
+        # style mixing maps a second latent batch (S3/training/loss.py:46-50): with merge_mapping_passes both batches go through
+        # the mapping network in one pass (rows are independent; w_avg tracks the first batch only)
+        self.merge_mapping_passes = merge_mapping_passes
 
     def run_G(self, z, c, update_emas=False):
+        if self.style_mixing_prob > 0 and self.merge_mapping_passes:
+            # same draws in the same order as below (the mapping network itself draws nothing); z and the mixing latents go
+            # through the mapping network as one batch, w_avg tracks the first half only
+            num_ws = self.G.mapping.num_ws
+            cutoff = torch.empty([], dtype=torch.int64, device=z.device).random_(1, num_ws)
+            cutoff = torch.where(torch.rand([], device=z.device) < self.style_mixing_prob, cutoff, torch.full_like(cutoff, num_ws))
+            both = self.G.mapping(torch.cat([z, torch.randn_like(z)]), torch.cat([c, c]), update_emas=update_emas, ema_rows=z.shape[0])
+            ws, ws2 = both[:z.shape[0]], both[z.shape[0]:]
+            layer = torch.arange(num_ws, device=z.device).reshape(1, -1, 1)
+            ws = torch.where(layer < cutoff, ws, ws2)
+            return self.G.synthesis(ws, update_emas=update_emas), ws
         ws = self.G.mapping(z, c, update_emas=update_emas)
         if self.style_mixing_prob > 0:
             cutoff = torch.empty([], dtype=torch.int64, device=ws.device).random_(1, ws.shape[1])

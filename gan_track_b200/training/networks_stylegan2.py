@@ -197,7 +197,9 @@ class MappingNetwork(torch.nn.Module):
         if num_ws is not None and w_avg_beta is not None:
             self.register_buffer('w_avg', torch.zeros([w_dim]))
 
-    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False):
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False, ema_rows=None):
+        # ema_rows (not in the reference): only the first `ema_rows` rows feed the w_avg update -- lets a caller map two latent
+        # batches in one pass while tracking the average of the first, as two separate calls would
         x = None
         if self.z_dim > 0:
             misc.assert_shape(z, [None, self.z_dim])
@@ -209,7 +211,7 @@ class MappingNetwork(torch.nn.Module):
         for idx in range(self.num_layers):
             x = getattr(self, f'fc{idx}')(x)
         if update_emas and self.w_avg_beta is not None:
-            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+            self.w_avg.copy_(x.detach()[:ema_rows].mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
         if self.num_ws is not None:
             x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
         if truncation_psi != 1:

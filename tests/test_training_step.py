@@ -92,6 +92,24 @@ def test_dmain_merged_pass_equals_two_passes():
         assert not tr.loss._can_merge_d(torch.zeros(4, 1, 16, 16), torch.zeros(4, 16))
 
 
+def test_style_mixing_single_mapping_pass_equals_two_passes():
+    """run_G with both latent batches through the mapping network at once: same images, same ws, same w_avg update."""
+    out = []
+    for merge in (False, True):
+        with oracle_ops():
+            tr = tl.Trainer(tiny_cfg(batch=4), rank=0, device='cpu', overlap=False)
+            tr.loss.merge_mapping_passes = merge
+            g = torch.Generator().manual_seed(13)
+            z = torch.randn([4, 16], generator=g)
+            c = torch.nn.functional.one_hot(torch.randint(0, 2, [4], generator=g), 2).float()
+            torch.manual_seed(21)
+            img, ws = tr.loss.run_G(z, c, update_emas=True)
+            out.append((img.detach(), ws.detach(), tr.G.mapping.w_avg.clone()))
+    for a, b, name in zip(out[0], out[1], ['img', 'ws', 'w_avg']):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), name
+    assert out[0][2].abs().sum() > 0
+
+
 def _worker(rank, world, port, overlap, out_dir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
