@@ -76,46 +76,6 @@ class FlatAdam:
         _lib.count_launch(2)
 
 
-    def step_scattered(self, key, active_idx, grads, grad_scale=1.0):
-        """Same update reading the gradients where autograd left them (one tensor per active parameter) instead of a
-        flattened copy: the chunk table addresses them relative to the lowest gradient address.  Single-GPU graph mode only --
-        the gradient tensors of a captured phase keep their addresses across replays, and there is no all-reduce that would
-        want one buffer; saves the 99 MB torch.cat per phase."""
-        active_idx = tuple(active_idx)
-        assert len(grads) == len(active_idx)
-        for g in grads:
-            assert g.dtype == torch.float32 and g.is_contiguous() and g.data_ptr() % 4 == 0
-        ptrs = tuple(g.data_ptr() for g in grads)
-        entry = self._tables.get(('scattered', key))
-        if entry is None or entry[0] != (active_idx, ptrs):
-            lib = _lib.load()
-            assert lib.gt_adam_chunk_bytes() == 24
-            rec = np.dtype([('pstart', '<i8'), ('gstart', '<i8'), ('count', '<i4'), ('seg', '<i4')])
-            base = min(ptrs)
-            rows = []
-            for i, ptr in zip(active_idx, ptrs):
-                n, poff, goff = self.fp.sizes[i], int(self.fp.offsets[i]), (ptr - base) // 4
-                for s0 in range(0, n, self.CHUNK):
-                    rows.append((poff + s0, goff + s0, min(self.CHUNK, n - s0), i))
-            dev = self.fp.flat.device
-            # pinned staging + asynchronous copy: legal inside a CUDA-graph capture (becomes a memcpy node; the pinned
-            # tensors are kept alive with the table)
-            host_chunks = torch.from_numpy(np.array(rows, dtype=rec).view(np.uint8).copy()).pin_memory()
-            host_active = torch.zeros([len(self.fp.params)], dtype=torch.int32)
-            host_active[list(active_idx)] = 1
-            host_active = host_active.pin_memory()
-            entry = ((active_idx, ptrs), host_chunks.to(dev, non_blocking=True), len(rows), host_active.to(dev, non_blocking=True), base,
-                     (host_chunks, host_active))
-            self._tables[('scattered', key)] = entry
-        _, chunks, nchunks, active, base, _ = entry
-        lib = _lib.load()
-        with torch.cuda.device(self.fp.flat.device):
-            _lib.check(lib.gt_adam_flat(_lib.ptr(self.fp.flat), base, _lib.ptr(self.m), _lib.ptr(self.v), _lib.ptr(self.steps),
-                                        _lib.ptr(active), len(self.fp.params), _lib.ptr(chunks), nchunks, self.lr, self.b1, self.b2, self.eps,
-                                        float(grad_scale), 1e5, -1e5, _lib.stream_of(self.fp.flat)), 'gt_adam_flat')
-        _lib.count_launch(2)
-
-
 def ema_update(ema_flat, src_flat, weight):
     """ema += weight * (src - ema) over whole flat parameter buffers (torch._foreach_lerp_(ema_params, src_params, weight))."""
     assert ema_flat.flat.numel() == src_flat.flat.numel()

@@ -339,18 +339,12 @@ class Trainer:
         phase.module.requires_grad_(False)
         st.with_grad = [p for p in phase.module.parameters() if p.grad is not None]
         st.active_idx = [i for i, p in enumerate(phase.module.parameters()) if p.grad is not None]
-        if self.num_gpus == 1 and phase.get('flat_opt') is not None and os.environ.get('GT_FLAT_CAT', '0') != '1' and all(p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in st.with_grad):
-            st.flat = None          # one GPU: nothing to exchange, the optimizer kernel reads the gradients in place
-        else:
-            st.flat = torch.cat([p.grad.flatten() for p in st.with_grad])
+        st.flat = torch.cat([p.grad.flatten() for p in st.with_grad])
 
     def _phase_half_b(self, phase, st):
         if phase.get('flat_opt') is not None:
             # /num_gpus, nan_to_num and Adam in one kernel over the flat gradient (parameters without a gradient are skipped)
-            if st.flat is None:
-                phase.flat_opt.step_scattered(phase.name, st.active_idx, [p.grad for p in st.with_grad], grad_scale=1.0)
-            else:
-                phase.flat_opt.step(phase.name, st.active_idx, st.flat, grad_scale=1.0 / self.num_gpus)
+            phase.flat_opt.step(phase.name, st.active_idx, st.flat, grad_scale=1.0 / self.num_gpus)
             return
         flat = st.flat
         if self.num_gpus > 1:

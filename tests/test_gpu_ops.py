@@ -472,45 +472,6 @@ def test_flat_adam_and_ema_match_torch():
         assert_close(p, r.detach().cpu(), 2e-6, 'ema param')
 
 
-def test_flat_adam_scattered_gradients_equal_flat_buffer():
-    """FlatAdam.step_scattered (gradients read where autograd left them, incl. inside a CUDA graph whose replays see new
-    gradient values at the captured addresses) == FlatAdam.step on the concatenated copy; the scrubbed gradients are written back."""
-    import copy
-    from gan_track_b200.training import flat_optim
-    torch.manual_seed(5)
-    net = torch.nn.Sequential(torch.nn.Linear(37, 129), torch.nn.Conv2d(3, 5, 3), torch.nn.Linear(11, 7, bias=False)).to(DEV)
-    ref = copy.deepcopy(net)
-    kw = dict(lr=0.002, betas=[0.0, 0.99], eps=1e-8)
-    fa, fb = flat_optim.FlatParams(net), flat_optim.FlatParams(ref)
-    oa, ob = flat_optim.FlatAdam(fa, **kw), flat_optim.FlatAdam(fb, **kw)
-    active = [0, 2, 3, 4]
-    shapes = [list(net.parameters())[i].shape for i in active]
-    grads = [torch.zeros(sh, device=DEV) for sh in shapes]            # static gradient tensors, as in a captured phase
-    pad = torch.zeros(1000, device=DEV)                                  # noqa: F841  (keeps the tensors from being adjacent)
-    src = [[torch.randn(sh, device=DEV) for sh in shapes] for _ in range(4)]
-    src[1][0][0, 0] = float('nan')
-    src[2][1].view(-1)[3] = float('-inf')
-    g = torch.cuda.CUDAGraph()
-    stream = torch.cuda.Stream()
-    stream.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(stream):
-        oa.step_scattered('main', active, grads, grad_scale=1.0)         # builds the table outside capture once (eager occurrence)
-    torch.cuda.current_stream().wait_stream(stream)
-    ob.step('main', active, torch.cat([t.flatten() for t in grads]), grad_scale=1.0)
-    with torch.cuda.graph(g):
-        oa.step_scattered('main', active, grads, grad_scale=1.0)
-    for it in range(4):
-        for t, v in zip(grads, src[it]):
-            t.copy_(v)
-        g.replay()
-        ob.step('main', active, torch.cat([t.flatten() for t in src[it]]), grad_scale=1.0)
-        for t, v in zip(grads, src[it]):
-            assert torch.equal(t, torch.nan_to_num(v, nan=0, posinf=1e5, neginf=-1e5))
-    torch.cuda.synchronize()
-    assert torch.equal(fa.flat, fb.flat)
-    assert torch.equal(oa.m, ob.m) and torch.equal(oa.v, ob.v) and torch.equal(oa.steps, ob.steps)
-
-
 # ---------------------------------------------------------------------------------------------------- FromRGB (1 channel)
 
 @pytest.mark.parametrize('dtype,C,act,clamp', [(torch.float16, 64, 'lrelu', 256.0), (torch.float16, 128, 'lrelu', 0.5), (torch.float32, 16, 'lrelu', None),
