@@ -39,6 +39,12 @@ _PROTOTYPES = {
     'gt_fc_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     'gt_fc_dgrad': (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'gt_fc_wgrad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    'gt_modprep_weight_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'gt_modprep_style_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'gt_modprep_rsqrt': (_i, [_vp, _vp, _i, _f, _vp]),
+    'gt_modprep_gq': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'gt_modprep_style_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'gt_modprep_weight_bwd': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gt_adam_chunk_bytes': (_i, []),
     'gt_adam_flat': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _vp]),
     'gt_ema_flat': (_i, [_vp, _vp, _ll, _f, _vp]),

@@ -240,3 +240,90 @@ def demod_act(x, d=None, noise=None, b=None, act='linear', alpha=0.2, gain=1.0, 
     [N,1,H,W] or None; b: [C] or None; act in {'linear', 'lrelu'}; clamp None or < 0 disables clamping."""
     assert act in _ACT
     return _DemodAct.apply(x, d, noise, b, act, float(alpha), float(gain), float(clamp) if clamp is not None else -1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parameter / style side: pre-normalisation + demodulation coefficients (csrc/modprep.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def prep_applicable(weight, styles):
+    """First-order passes only: the path-length pass differentiates this backward and keeps the tensor-op form
+    (`rgb.op_by_op_torgb` is the switch the loss flips for that pass)."""
+    from . import rgb
+    return (rgb.torgb_fused and weight.is_cuda and weight.dtype == torch.float32 and styles.dtype == torch.float32 and styles.ndim == 2
+            and weight.ndim == 4 and 1 <= styles.shape[0] <= 64 and weight.shape[1] % 4 == 0 and styles.shape[1] == weight.shape[1])
+
+
+class _ModPrep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, styles, prenorm):
+        from . import fc
+        lib = _lib.load()
+        O, I, kh, kw = weight.shape
+        N = styles.shape[0]
+        W, s = weight.contiguous(), styles.contiguous()
+        dev = W.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        wsq, sn2 = torch.empty([O, I], **f32), torch.empty([N, I], **f32)
+        w16 = scale = amax = smax = sarg = None
+        sn = s
+        if prenorm:
+            w16 = torch.empty([O, I, kh, kw], dtype=torch.float16, device=dev)
+            scale, smax = torch.empty([O], **f32), torch.empty([N], **f32)
+            amax, sarg = torch.empty([O], dtype=torch.int32, device=dev), torch.empty([N], dtype=torch.int32, device=dev)
+            sn = torch.empty([N, I], **f32)
+        with torch.cuda.device(dev):
+            st = _lib.stream_of(W)
+            _lib.check(lib.gt_modprep_weight_fwd(_lib.ptr(W), _lib.ptr(w16), _lib.ptr(wsq), _lib.ptr(scale), _lib.ptr(amax), O, I, kh * kw, int(prenorm), st),
+                       'gt_modprep_weight_fwd')
+            _lib.check(lib.gt_modprep_style_fwd(_lib.ptr(s), _lib.ptr(sn) if prenorm else None, _lib.ptr(sn2), _lib.ptr(smax), _lib.ptr(sarg), N, I,
+                                                int(prenorm), st), 'gt_modprep_style_fwd')
+            q = fc._fwd(sn2, wsq, None, 1.0, 0.0)                                # [N, O]
+            d = torch.empty_like(q)
+            _lib.check(lib.gt_modprep_rsqrt(_lib.ptr(q), _lib.ptr(d), N * O, 1e-8, st), 'gt_modprep_rsqrt')
+        _lib.count_launch(3)
+        ctx.save_for_backward(W, sn, sn2, wsq, d, scale, amax, smax, sarg)
+        ctx.prenorm = bool(prenorm)
+        ctx.wshape = weight.shape
+        return (w16, sn, d) if prenorm else (None, None, d)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_w, g_sn, g_d):
+        from . import fc
+        lib = _lib.load()
+        W, sn, sn2, wsq, d, scale, amax, smax, sarg = ctx.saved_tensors
+        O, I, kh, kw = ctx.wshape
+        N = sn.shape[0]
+        if g_d is None:
+            g_d = torch.zeros_like(d)
+        g_d = g_d.contiguous().to(torch.float32)
+        gq = torch.empty_like(d)
+        gW = gs = None
+        with torch.cuda.device(W.device):
+            st = _lib.stream_of(W)
+            _lib.check(lib.gt_modprep_gq(_lib.ptr(d), _lib.ptr(g_d), _lib.ptr(gq), N * O, st), 'gt_modprep_gq')
+            _lib.count_launch()
+            if ctx.needs_input_grad[1]:
+                t = fc._dgrad(gq, wsq, 1.0)                                      # [N, I]
+                g_sn = g_sn.contiguous().to(torch.float32) if g_sn is not None else None
+                gs = torch.empty_like(sn)
+                _lib.check(lib.gt_modprep_style_bwd(_lib.ptr(g_sn), _lib.ptr(sn), _lib.ptr(t), _lib.ptr(smax), _lib.ptr(sarg), _lib.ptr(gs), N, I,
+                                                    int(ctx.prenorm), st), 'gt_modprep_style_bwd')
+                _lib.count_launch()
+            if ctx.needs_input_grad[0]:
+                g_wsq = fc._wgrad(gq, sn2, 1.0, 0.0, False)[0]                   # [O, I]
+                g_w = g_w.contiguous() if g_w is not None else None
+                gW = torch.empty_like(W)
+                _lib.check(lib.gt_modprep_weight_bwd(_lib.ptr(W), _lib.ptr(g_w), _lib.dtype_code(g_w) if g_w is not None else 0, _lib.ptr(g_wsq),
+                                                     _lib.ptr(scale), _lib.ptr(amax), _lib.ptr(gW), O, I, kh * kw, int(ctx.prenorm), st), 'gt_modprep_weight_bwd')
+                _lib.count_launch()
+                gW = gW.reshape(ctx.wshape)
+        return gW, gs, None
+
+
+def prep(weight, styles, prenorm):
+    """(weight_scaled_fp16 | None, styles_normalised | None, dcoefs): the pre-normalised operands (fp16 layers) and the
+    demodulation coefficients of modulated_conv2d (S3/training/networks_stylegan2.py:52-63), differentiable once w.r.t. weight
+    and styles."""
+    return _ModPrep.apply(weight, styles, bool(prenorm))

@@ -44,6 +44,7 @@ class FlatAdam:
     def _table(self, key, active_idx):
         """(chunk records, active flags) for one phase: chunks of <= CHUNK elements that never straddle a parameter, with the
         parameter's offset in the flat parameter buffer and in the phase's compact gradient buffer."""
+        key = (key, tuple(active_idx))
         if key in self._tables:
             return self._tables[key]
         lib = _lib.load()

@@ -43,12 +43,17 @@ def modulated_conv2d(
 
     # fp16: pre-normalise so that neither the scaled activations nor the conv overflow; demodulation makes the result
     # invariant to both scalings.
-    if x.dtype == torch.float16 and demodulate:
+    dcoefs = None
+    if demodulate and not fused_modconv and modulated.prep_applicable(weight, styles):
+        # pre-normalisation and demodulation coefficients in four launches (csrc/modprep.cu) instead of ~13 tensor ops
+        w16, sn, dcoefs = modulated.prep(weight, styles, x.dtype == torch.float16)
+        if x.dtype == torch.float16:
+            weight, styles = w16, sn
+    elif x.dtype == torch.float16 and demodulate:
         weight = weight * (1 / np.sqrt(in_channels * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
         styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
 
-    dcoefs = None
-    if demodulate:
+    if demodulate and dcoefs is None:
         # rsqrt(sum_i s[n,i]^2 * sum_k W[o,i,k]^2 + eps): identical to reducing the [N,O,I,kh,kw] product
         # (reference :60-63) without materialising it.
         wsq = weight.square().sum(dim=[2, 3])                                   # [O, I]

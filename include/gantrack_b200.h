@@ -146,6 +146,27 @@ int gt_fc_fwd(const float* x, const float* w, const float* b, float* y, int M, i
 int gt_fc_dgrad(const float* dy, const float* w, float* dx, int M, int I, int O, float wgain, void* stream);
 int gt_fc_wgrad(const float* dy, const float* x, float* dw, float* db, int M, int I, int O, float wgain, float bgain, void* stream);
 
+/* ---- parameter / style side of the training-mode modulated convolution ----------------------------------------------
+ * Replaces the tensor-op chain of modulated_conv2d (S3/training/networks_stylegan2.py:52-63): fp16 pre-normalisation
+ * `weight * (1/sqrt(I*KK) / weight.norm(inf, dim=[1,2,3]))`, `styles / styles.norm(inf, dim=1)` and the demodulation
+ * coefficients `rsqrt(styles^2 @ wsq^T + eps)`, wsq[o,i] = sum_k weight[o,i,k]^2, plus their vector-Jacobian products.
+ * All tensors contiguous; W [O,I,KK] fp32, styles [N,I] fp32.  prenorm = 0: scale = 1, no max terms, w16 / sn / scale /
+ * amax / smax / sarg may be NULL (sn := s).  The matrix products in between are gt_fc_fwd / gt_fc_wgrad / gt_fc_dgrad.
+ *   gt_modprep_weight_fwd:  w16 = fp16(W * scale[o]), wsq, scale[o] = (1/sqrt(I*KK)) / max|W[o]|, amax[o] = argmax
+ *   gt_modprep_style_fwd:   sn = s / max|s[n]|, sn2 = sn^2, smax, sarg
+ *   gt_modprep_rsqrt:       d = rsqrt(q + eps)
+ *   gt_modprep_gq:          gq = -1/2 d^3 gd
+ *   gt_modprep_style_bwd:   gs from g_sn (may be NULL), t = gq @ wsq
+ *   gt_modprep_weight_bwd:  gW from g_w (gradient w.r.t. the scaled weight, dtype code g_w_dtype, may be NULL) and g_wsq */
+int gt_modprep_weight_fwd(const float* W, void* w16, float* wsq, float* scale, int* amax, int O, int I, int KK, int prenorm, void* stream);
+int gt_modprep_style_fwd(const float* s, float* sn, float* sn2, float* smax, int* sarg, int N, int I, int prenorm, void* stream);
+int gt_modprep_rsqrt(const float* q, float* d, int n, float eps, void* stream);
+int gt_modprep_gq(const float* d, const float* gd, float* gq, int n, void* stream);
+int gt_modprep_style_bwd(const float* g_sn, const float* sn, const float* t, const float* smax, const int* sarg, float* gs, int N, int I, int prenorm,
+                         void* stream);
+int gt_modprep_weight_bwd(const float* W, const void* g_w, int g_w_dtype, const float* g_wsq, const float* scale, const int* amax, float* gW, int O, int I,
+                          int KK, int prenorm, void* stream);
+
 /* ---- parameter update on flat buffers ------------------------------------------------------
  * A module's parameters, gradients and Adam moments are views into flat fp32 buffers.  gt_adam_flat fuses the gradient
  * exchange epilogue (x grad_scale = 1/num_gpus, nan_to_num(0, posinf, neginf)) with torch.optim.Adam's update

@@ -125,3 +125,86 @@ def test_synthesis_layer_fused_vs_unfused_vs_fp32():
         for i, (t, a, b_) in enumerate(zip(res['fp32'], res['fused'], res['unfused'])):
             ef, eu = _rel(a, t), _rel(b_, t)
             assert ef <= max(1e-2, 1.25 * eu), f'up={up} output {i}: fused {ef:.3e} unfused {eu:.3e}'
+
+
+def _ref_prep(weight, styles, prenorm):
+    """The reference's tensor-op chain (S3/training/networks_stylegan2.py:52-63)."""
+    O, I, kh, kw = weight.shape
+    w16 = sn = None
+    if prenorm:
+        weight = weight * (1 / np.sqrt(I * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+        styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
+        w16, sn = weight.to(torch.float16), styles
+    wsq = weight.square().sum(dim=[2, 3])
+    return w16, sn, (styles.square() @ wsq.t() + 1e-8).rsqrt()
+
+
+@pytest.mark.parametrize('N,O,I,k,prenorm', [(32, 512, 512, 3, True), (32, 64, 128, 3, True), (16, 256, 512, 3, False), (8, 512, 512, 3, False),
+                                             (5, 72, 36, 1, True), (64, 128, 64, 3, True)])
+def test_modprep_matches_tensor_ops(N, O, I, k, prenorm):
+    """csrc/modprep.cu (pre-normalisation + demodulation coefficients in four launches) against the reference's op chain: the
+    scaled fp16 weight and normalised styles bit for bit, dcoefs to fp32 rounding, and the gradients w.r.t. weight and styles
+    for random upstream gradients of all three outputs."""
+    from gan_track_b200.torch_utils.ops import modulated
+    torch.manual_seed(N + O)
+    weight = torch.randn(O, I, k, k, device='cuda').requires_grad_(True)
+    styles = (torch.randn(N, I, device='cuda') * 1.5 + 1).requires_grad_(True)
+    assert modulated.prep_applicable(weight, styles)
+    w16, sn, d = modulated.prep(weight, styles, prenorm)
+    rw, rs, rd = _ref_prep(weight, styles, prenorm)
+    if prenorm:
+        assert torch.equal(w16, rw) and torch.equal(sn, rs)
+    else:
+        assert w16 is None and sn is None
+    assert _rel(d, rd) <= 2e-6
+    g_d = torch.randn_like(d)
+    outs, routs, gouts = [d], [rd], [g_d]
+    if prenorm:
+        g_w = (torch.randn_like(w16.float()) * 0.1).half()
+        g_s = torch.randn_like(sn)
+        outs, routs, gouts = [w16, sn, d], [rw, rs, rd], [g_w, g_s, g_d]
+    gW, gs = torch.autograd.grad(outs, [weight, styles], gouts)
+    rW, rgs = torch.autograd.grad(routs, [weight, styles], gouts)
+    assert _rel(gW, rW) <= 1e-5, _rel(gW, rW)
+    assert _rel(gs, rgs) <= 1e-5, _rel(gs, rgs)
+    # only dcoefs used downstream (no gradient reaches the other outputs)
+    w16, sn, d = modulated.prep(weight, styles, prenorm)
+    gW2, gs2 = torch.autograd.grad([d], [weight, styles], [g_d])
+    rW2, rgs2 = torch.autograd.grad([_ref_prep(weight, styles, prenorm)[2]], [weight, styles], [g_d])
+    assert _rel(gW2, rW2) <= 1e-5 and _rel(gs2, rgs2) <= 1e-5
+    # first-order only: asking for a differentiable backward must fail loudly, and the path-length switch restores the op chain
+    w16, sn, d = modulated.prep(weight, styles, prenorm)
+    with pytest.raises(RuntimeError):
+        g, = torch.autograd.grad([d.sum()], [styles], create_graph=True)
+        g.sum().backward()
+    from gan_track_b200.torch_utils.ops import rgb
+    with rgb.op_by_op_torgb():
+        assert not modulated.prep_applicable(weight, styles)
+
+
+@pytest.mark.parametrize('dtype,C', [(torch.float16, 64), (torch.float32, 32)])
+def test_modulated_conv2d_prep_route_equals_op_chain(dtype, C):
+    """modulated_conv2d through the fused preparation vs the tensor-op chain (selected by the path-length switch): output and
+    the gradients of x, weight, styles."""
+    from gan_track_b200.torch_utils.ops import rgb
+    from gan_track_b200.training import networks_stylegan2 as nets
+    torch.manual_seed(7)
+    x = _cl(torch.randn(4, C, 32, 32, device='cuda').to(dtype)).requires_grad_(True)
+    weight = torch.randn(2 * C, C, 3, 3, device='cuda').requires_grad_(True)
+    styles = (torch.randn(4, C, device='cuda') + 1).requires_grad_(True)
+    noise = torch.randn(4, 1, 32, 32, device='cuda')
+    res = []
+    for fused in (True, False):
+        ctx = rgb.op_by_op_torgb() if not fused else None
+        if ctx is not None:
+            ctx.__enter__()
+        try:
+            y = nets.modulated_conv2d(x, weight, styles, noise=noise, padding=1, fused_modconv=False)
+        finally:
+            if ctx is not None:
+                ctx.__exit__()
+        dy = torch.randn(y.shape, device='cuda', generator=torch.Generator('cuda').manual_seed(1)).to(dtype)
+        res.append((y.detach(),) + torch.autograd.grad(y, [x, weight, styles], dy))
+    tol = 1e-2 if dtype == torch.float16 else 1e-5
+    for a, b, name in zip(res[0], res[1], ['y', 'gx', 'gw', 'gs']):
+        assert _rel(a, b) <= tol, (name, _rel(a, b))
