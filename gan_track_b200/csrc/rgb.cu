@@ -258,9 +258,7 @@ __global__ void __launch_bounds__(256) torgb1_bwd_kernel(const T* __restrict__ d
     const T* xn = x + (long long)n * P * C;
     T* dxn = dx + (long long)n * P * C;
     const T* dyn = dy + (long long)n * P;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const float g = (float)to_acc<T>(dyn[(i >> lcv)]);
-        const Vec16<T> xv = ld16_stream(xn + i * VEC);
+    auto body = [&](long long i, float g, const Vec16<T>& xv) {
         Vec16<T> o;
 #pragma unroll
         for (int k = 0; k < L::NP; k++) {
@@ -275,7 +273,17 @@ __global__ void __launch_bounds__(256) torgb1_bwd_kernel(const T* __restrict__ d
         }
         if (cv == 0) ab += g;
         st16_stream(dxn + i * VEC, o);
+    };
+    // two vectors per iteration: twice the loads in flight per thread (the pass is latency-bound at 8 warps per CTA otherwise)
+    const long long step = (long long)gridDim.x * 256;
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (; i + step < total; i += 2 * step) {
+        const float g0 = (float)to_acc<T>(dyn[(i >> lcv)]), g1 = (float)to_acc<T>(dyn[((i + step) >> lcv)]);
+        const Vec16<T> x0 = ld16_stream(xn + i * VEC), x1 = ld16_stream(xn + (i + step) * VEC);
+        body(i, g0, x0);
+        body(i + step, g1, x1);
     }
+    if (i < total) body(i, (float)to_acc<T>(dyn[(i >> lcv)]), ld16_stream(xn + i * VEC));
     float* out = partial + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
 #pragma unroll
     for (int pass = 0; pass < 2; pass++) {
@@ -302,25 +310,28 @@ __global__ void __launch_bounds__(256) torgb1_bwd_kernel(const T* __restrict__ d
 }
 
 // ds[n][c] = sum_band partial[n][band][0][c];  dw[c] = sum_n sum_band partial[n][band][1][c];  db = sum partial_b   (fixed order)
-__global__ void torgb1_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b, float* __restrict__ ds, float* __restrict__ dw,
-                                     float* __restrict__ db, int N, int C, int bands) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N * C) {
-        const int n = i / C, c = i - n * C;
-        float sum = 0.f;
-        for (int b = 0; b < bands; b++) sum += partial[((long long)n * bands + b) * 2 * C + c];
-        ds[i] = sum;
+// one warp per output value (ds[n,c]: `bands` terms; dw[c], db: N * bands terms), lanes stride over the terms, fixed order
+__global__ void __launch_bounds__(256) torgb1_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b, float* __restrict__ ds,
+                                                            float* __restrict__ dw, float* __restrict__ db, int N, int C, int bands) {
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int nds = N * C;
+    float sum = 0.f;
+    if (o < nds) {
+        const int n = o / C, c = o - n * C;
+        for (int b = lane; b < bands; b += 32) sum += partial[((long long)n * bands + b) * 2 * C + c];
+    } else if (o < nds + C) {
+        const int c = o - nds;
+        for (int k = lane; k < N * bands; k += 32) sum += partial[(long long)k * 2 * C + C + c];
+    } else if (o == nds + C) {
+        for (int k = lane; k < N * bands; k += 32) sum += partial_b[k];
+    } else {
+        return;
     }
-    if (i < C) {
-        float sum = 0.f;
-        for (int n = 0; n < N; n++)
-            for (int b = 0; b < bands; b++) sum += partial[((long long)n * bands + b) * 2 * C + C + i];
-        dw[i] = sum;
-    }
-    if (i == 0) {
-        float sum = 0.f;
-        for (int k = 0; k < N * bands; k++) sum += partial_b[k];
-        db[0] = sum;
+    sum = warp_sum(sum);
+    if (lane == 0) {
+        if (o < nds) ds[o] = sum;
+        else if (o < nds + C) dw[o - nds] = sum;
+        else db[0] = sum;
     }
 }
 
@@ -368,8 +379,8 @@ extern "C" int gt_torgb1_bwd(const void* dy, const void* x, const float* s, cons
     else
         torgb1_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)x, s, (const float*)w, (float*)dx, part, part_b, P, C);
     GT_CUDA_LAUNCH_CHECK("gt_torgb1_bwd");
-    const int total = N * C;
-    torgb1_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(part, part_b, ds, dw, db, N, C, bands);
+    const int total = N * C + C + 1;
+    torgb1_reduce_kernel<<<(total + 7) / 8, 256, 0, st>>>(part, part_b, ds, dw, db, N, C, bands);
     GT_CUDA_LAUNCH_CHECK("gt_torgb1_bwd(reduce)");
     return GT_OK;
 }
