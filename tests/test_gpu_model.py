@@ -46,7 +46,16 @@ def test_networks_fp32_vs_reference_golden(models32):
     G, gen, dis = models32
     z, c, real = t(G['model/z']), t(G['model/c']), t(G['model/real'])
     gen.eval()
+    # the reference's eval-mode output (its grouped fused_modconv branch) vs both of our evaluations of that branch: the
+    # default shared-weight route and the grouped convolution
     assert rel_err(gen(z, c, noise_mode='const'), G['model/G_eval_const']) <= 2e-5
+    nets.grouped_fused_modconv = True
+    try:
+        assert rel_err(gen(z, c, noise_mode='const'), G['model/G_eval_const']) <= 2e-5
+        assert rel_err(gen(z[:1], c[:1], noise_mode='const'), G['model/G_eval_const'][:1]) <= 2e-5
+    finally:
+        nets.grouped_fused_modconv = False
+    assert rel_err(gen(z[:1], c[:1], noise_mode='const'), G['model/G_eval_const'][:1]) <= 2e-5       # batch 1
     gen.train()
     assert rel_err(gen(z, c, noise_mode='const'), G['model/G_train_const']) <= 2e-5
     assert rel_err(dis(real, c), G['model/D_real']) <= 2e-5
@@ -168,10 +177,13 @@ def test_trainer_cuda_graph_mode_runs_and_captures():
         assert torch.isfinite(p).all()
 
 
-@pytest.mark.parametrize('fp32,tol', [(True, 2e-5), (False, 2e-2)])
+@pytest.mark.parametrize('fp32,tol', [(True, 2e-4), (False, 2e-2)])
 def test_dmain_merged_pass_equals_two_passes_cuda(fp32, tol):
     """Dmain as one discriminator pass over the interleaved [generated, real] batch vs the reference's two passes, on the
-    CUDA kernels (fp32 model and fp16 model on the tcgen05 path): same parameter gradients up to summation order."""
+    CUDA kernels (fp32 model and fp16 model on the tcgen05 path): same parameter gradients up to summation order.  The fp32
+    bound is 2e-4, not 1e-5: weight gradients are sums over 10^5..10^6 mixed-sign terms whose grouping differs between one pass
+    over 2N samples and two passes over N (observed up to 4e-5 on fromrgb.weight, varying with the library's algorithm choice);
+    the exact equivalence of the schedule is pinned at 1e-5 by the CPU test (tests/test_training_step.py)."""
     from gan_track_b200.training import training_loop as tl
     grads = []
     for merge in (False, True):
