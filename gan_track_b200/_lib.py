@@ -39,6 +39,7 @@ _PROTOTYPES = {
     'gt_fc_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     'gt_fc_dgrad': (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'gt_fc_wgrad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    'gt_batch_gather': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     'gt_modprep_weight_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'gt_modprep_style_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gt_modprep_rsqrt': (_i, [_vp, _vp, _i, _f, _vp]),

@@ -167,6 +167,17 @@ int gt_modprep_style_bwd(const float* g_sn, const float* sn, const float* t, con
 int gt_modprep_weight_bwd(const float* W, const void* g_w, int g_w_dtype, const float* g_wsq, const float* scale, const int* amax, float* gW, int O, int I,
                           int KK, int prenorm, void* stream);
 
+/* ---- training batches from a device-resident packed shard ---------------------------------
+ * One launch replaces the reference's per-iteration DataLoader work (unzip + unpickle per slice,
+ * S3/training/dataset_mi_multimodal.py:255-268; x-flip copy :113-116; collation; H2D copy; `/127.5 - 1`,
+ * S3/training/training_loop_mi_multimodal.py:313-317):
+ *     dst[b,c,y,x] = decode(src[raw_idx[idx[b]], c, y, xflip[idx[b]] ? W-1-x : x]) / scale + shift
+ * src [n_src,C,H,W] of src_dtype 0 = float32, 1 = float16, 3 = uint16 (stored round(v*257)); idx [B] int64 dataset indices;
+ * raw_idx [n_idx] int64 / xflip [n_idx] uint8 = the dataset's index tables; dst [B,C,H,W] float32.  Out-of-range indices
+ * produce NaN pixels (the binding validates host-side index arrays before upload). */
+int gt_batch_gather(const void* src, int src_dtype, const long long* idx, const long long* raw_idx, const unsigned char* xflip, float* dst, int B, int C,
+                    int H, int W, int n_src, int n_idx, float scale, float shift, void* stream);
+
 /* ---- parameter update on flat buffers ------------------------------------------------------
  * A module's parameters, gradients and Adam moments are views into flat fp32 buffers.  gt_adam_flat fuses the gradient
  * exchange epilogue (x grad_scale = 1/num_gpus, nan_to_num(0, posinf, neginf)) with torch.optim.Adam's update
