@@ -78,7 +78,15 @@ def modulated_conv2d(
             x = modulated.mod_scale(x, styles)                                   # one pass forward, one pass backward (gx and gs)
         else:
             x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
-        x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
+        if (out_channels == 1 and kh == 1 and kw == 1 and up == 1 and down == 1 and padding == 0 and x.is_cuda and x.dim() == 4
+                and x.stride(1) == 1 and x.is_contiguous(memory_format=torch.channels_last)):
+            # ToRGB to one image channel on a channels-last tensor is a per-pixel dot product: [N,H,W,C] @ [C,1] on a free view.
+            # Same rounding points as the 1x1 convolution (fp32 accumulation, one rounding of the result) and differentiable to
+            # any order by autograd -- this is the form the path-length pass uses; the library's convolution for Cout = 1 costs
+            # two fp32 kernels of 470 us plus format copies there.
+            x = torch.matmul(x.permute(0, 2, 3, 1), weight.to(x.dtype).reshape(in_channels, 1)).permute(0, 3, 1, 2)
+        else:
+            x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
         if bias_act_args is not None and bias_act_args['act'] in ('linear', 'lrelu') and modulated.applicable(x):
             spec = bias_act.activation_funcs[bias_act_args['act']]
             gain = bias_act_args['gain'] if bias_act_args['gain'] is not None else spec.def_gain

@@ -535,3 +535,29 @@ def test_torgb1_matches_modulated_conv_bias_act(dtype, C, clamp):
     for i, (a, c) in enumerate(zip(outs[0], outs[1])):
         assert a.shape == c.shape
         assert_close(a.float(), c.float().cpu(), tol if i != 4 else 10 * tol, f'torgb1 output {i}')
+
+
+def test_torgb_op_by_op_matmul_route_matches_convolution_route():
+    """The path-length pass keeps ToRGB in op-by-op form; on channels-last tensors its 1x1 convolution to one channel runs as a
+    per-pixel matmul on a free view.  Same values / first- and second-order gradients as the convolution route (NCHW input)."""
+    from gan_track_b200.torch_utils.ops import rgb
+    from gan_track_b200.training import networks_stylegan2 as nets
+    torch.manual_seed(11)
+    layer = nets.ToRGBLayer(64, 1, w_dim=32, conv_clamp=256, channels_last=True).to(DEV)
+    x0 = torch.randn(3, 64, 24, 20, device=DEV).half()
+    w0 = torch.randn(3, 32, device=DEV)
+    probe = torch.randn(3, 1, 24, 20, device=DEV)
+    res = []
+    for cl in (True, False):
+        x = (x0.contiguous(memory_format=torch.channels_last) if cl else x0.contiguous()).requires_grad_(True)
+        w = w0.clone().requires_grad_(True)
+        with rgb.op_by_op_torgb():
+            y = layer(x, w, fused_modconv=False)
+            gw, = torch.autograd.grad((y.float() * probe).sum(), [w], create_graph=True)
+            pen = gw.square().sum()
+            g2 = torch.autograd.grad(pen, [x, w, layer.weight, layer.affine.weight], allow_unused=True)
+        # y is linear in the styles, so d(pen)/dw vanishes: autograd reports it as None on one route and as zeros on the other
+        assert g2[1] is None or float(g2[1].abs().max()) == 0.0
+        res.append((y.detach(), gw.detach(), g2[0], g2[2], g2[3]))
+    for a, b in zip(res[0], res[1]):
+        assert_close(a, b, 1e-2)
