@@ -421,6 +421,10 @@ class SynthesisNetwork(torch.nn.Module):
     def forward(self, ws, **block_kwargs):
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
         ws = ws.to(torch.float32)
+        if ws.is_cuda:
+            # one [num_ws, N, w_dim] copy, handed to the blocks as [N, n, w_dim] views whose per-layer slices are contiguous rows:
+            # the style affines read them in place instead of 20 per-layer .contiguous() copies (same values)
+            ws = ws.transpose(0, 1).contiguous().transpose(0, 1)
         block_ws = []
         w_idx = 0
         for res in self.block_resolutions:
