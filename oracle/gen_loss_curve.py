@@ -25,7 +25,7 @@ G_REG, D_REG = 4, 16
 STATS = ['Loss/G/loss', 'Loss/D/loss', 'Loss/pl_penalty', 'Loss/r1_penalty', 'Loss/scores/fake', 'Loss/scores/real']
 
 
-def run_curve(networks, loss_mod, training_stats, golden_model, device='cpu', probe=None, iters=ITERS, G_kw=None, D_kw=None):
+def run_curve(networks, loss_mod, training_stats, golden_model, device='cpu', probe=None, iters=ITERS, G_kw=None, D_kw=None, loss_extra=None):
     """One fixed-seed run; `networks` / `loss_mod` / `training_stats` are either the reference's modules or ours."""
     dev = torch.device(device)
     torch.manual_seed(SEED)            # (initial weights when no golden state is given; the CPU generator, so device-independent)
@@ -35,7 +35,7 @@ def run_curve(networks, loss_mod, training_stats, golden_model, device='cpu', pr
         G.load_state_dict({k[len('model/G/'):]: torch.from_numpy(golden_model[k]) for k in golden_model.files if k.startswith('model/G/')})
         D.load_state_dict({k[len('model/D/'):]: torch.from_numpy(golden_model[k]) for k in golden_model.files if k.startswith('model/D/')})
     G, D = G.to(dev), D.to(dev)
-    loss = loss_mod.StyleGAN2Loss(device=dev, G=G, D=D, augment_pipe=None, **LOSS_KW)
+    loss = loss_mod.StyleGAN2Loss(device=dev, G=G, D=D, augment_pipe=None, **LOSS_KW, **(loss_extra or {}))     # loss_extra: schedule options of OUR loss only
     phases = []
     for name, module, interval in [('G', G, G_REG), ('D', D, D_REG)]:
         ratio = interval / (interval + 1)
