@@ -28,6 +28,7 @@ x256 = t([32, 256, 64, 64]); w256 = t([256, 256, 3, 3]) * 0.02            # G b6
 x64 = t([32, 64, 256, 256]); w64 = t([64, 64, 3, 3]) * 0.04               # G b256 conv1 / D b256 conv0
 x128 = t([32, 128, 128, 128]); wT = t([128, 64, 3, 3]) * 0.03             # G b256 conv0 (transposed stride 2)
 xb = t([32, 64, 257, 257])
+xu = t([32, 64, 128, 128])                                                # backward of the D skip downsample
 f = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
 b = torch.randn([64], device=dev, dtype=torch.float16)
 pipe = augment.AugmentPipe(xflip=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1)
@@ -48,6 +49,7 @@ for _ in range(a.reps + 1):
     conv_igemm.igemm_wgrad(x64, x64, (64, 64, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     upfirdn2d.upfirdn2d(xb, f, padding=[1, 1, 1, 1], gain=4)
     upfirdn2d.upfirdn2d(x64, f, down=2, padding=[1, 1, 1, 1])
+    upfirdn2d.upfirdn2d(xu, f, up=2, padding=[2, 1, 2, 1], gain=4)
     upfirdn2d.upfirdn2d(xp32, f, padding=[1, 1, 1, 1], gain=4)
     xg = x64.clone().requires_grad_(True)
     bg = b.clone().requires_grad_(True)
