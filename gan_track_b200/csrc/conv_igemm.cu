@@ -191,11 +191,6 @@ __global__ void pack_weight_kernel(const __half* __restrict__ w, long long s_co,
     }
 }
 
-int ilog2_floor(int v) {
-    int l = 0;
-    while ((1 << (l + 1)) <= v) l++;
-    return l;
-}
 int next_pow2_log2(int v) {
     int l = 0;
     while ((1 << l) < v) l++;
