@@ -25,48 +25,40 @@ from .. import _lib
 from .. import dnnlib
 
 
+def _index_tables(n_raw, max_size, xflip, random_seed):
+    """(raw_idx int64, flip uint8): which stored slice each dataset item is and whether it is mirrored.  `max_size` keeps a seeded
+    random subset in storage order; `xflip` appends a mirrored copy of the (sub)set (reference :57-68)."""
+    raw = np.arange(n_raw, dtype=np.int64)
+    if max_size is not None and n_raw > max_size:
+        np.random.RandomState(random_seed).shuffle(raw)
+        raw = np.sort(raw[:max_size])
+    flip = np.zeros(raw.size, dtype=np.uint8)
+    if xflip:
+        raw, flip = np.tile(raw, 2), np.concatenate([flip, np.ones_like(flip)])
+    return raw, flip
+
+
 class Dataset(torch.utils.data.Dataset):
+    """Item contract of the reference's base class: `ds[i] -> (image CHW, label, fname)`; subclasses provide `_load_raw_image(raw_idx)
+    -> (CHW array, fname)` and `_load_raw_labels() -> [N] int64 | [N,L] float32 | None`."""
+
     def __init__(self, name, raw_shape, dtype, max_size=None, use_labels=False, xflip=False, split='train', modalities=None, random_seed=0):
-        self._name = name
-        self._dtype = dtype
-        self._split = split
+        self._name, self._dtype, self._split = name, dtype, split
         self._modalities = ['MR_nonrigid_CT', 'MR_MR_T2'] if modalities is None else modalities
         self._raw_shape = list(raw_shape)
         self._use_labels = use_labels
-        self._raw_labels = None
-        self._label_shape = None
-        # max_size: a seeded random subset, kept in raw order; applied before the flip doubling (reference :59-62)
-        self._raw_idx = np.arange(self._raw_shape[0], dtype=np.int64)
-        if max_size is not None and self._raw_idx.size > max_size:
-            np.random.RandomState(random_seed).shuffle(self._raw_idx)
-            self._raw_idx = np.sort(self._raw_idx[:max_size])
-        self._xflip = np.zeros(self._raw_idx.size, dtype=np.uint8)
-        if xflip:
-            self._raw_idx = np.tile(self._raw_idx, 2)
-            self._xflip = np.concatenate([self._xflip, np.ones_like(self._xflip)])
+        self._raw_labels = self._label_shape = None
+        self._raw_idx, self._xflip = _index_tables(self._raw_shape[0], max_size, xflip, random_seed)
 
-    def _get_raw_labels(self):
-        if self._raw_labels is None:
-            self._raw_labels = self._load_raw_labels() if self._use_labels else None
-            if self._raw_labels is None:
-                self._raw_labels = np.zeros([self._raw_shape[0], 0], dtype=np.float32)
-            assert isinstance(self._raw_labels, np.ndarray) and self._raw_labels.shape[0] == self._raw_shape[0]
-            assert self._raw_labels.dtype in [np.float32, np.int64]
-            if self._raw_labels.dtype == np.int64:
-                assert self._raw_labels.ndim == 1 and np.all(self._raw_labels >= 0)
-        return self._raw_labels
-
-    def close(self):
-        pass
-
+    # -- subclass hooks -------------------------------------------------------------------------------------------
     def _load_raw_image(self, raw_idx):
         raise NotImplementedError
 
     def _load_raw_labels(self):
         raise NotImplementedError
 
-    def __getstate__(self):
-        return dict(self.__dict__, _raw_labels=None)
+    def close(self):
+        pass
 
     def __del__(self):
         try:
@@ -74,6 +66,55 @@ class Dataset(torch.utils.data.Dataset):
         except Exception:  # noqa: BLE001
             pass
 
+    def __getstate__(self):
+        return dict(self.__dict__, _raw_labels=None)        # labels are re-read lazily in worker processes
+
+    # -- labels ---------------------------------------------------------------------------------------------------
+    def _get_raw_labels(self):
+        if self._raw_labels is None:
+            lab = self._load_raw_labels() if self._use_labels else None
+            if lab is None:
+                lab = np.zeros([self._raw_shape[0], 0], dtype=np.float32)
+            assert isinstance(lab, np.ndarray) and lab.shape[0] == self._raw_shape[0] and lab.dtype in [np.float32, np.int64]
+            if lab.dtype == np.int64:
+                assert lab.ndim == 1 and np.all(lab >= 0)
+            self._raw_labels = lab
+        return self._raw_labels
+
+    @property
+    def has_onehot_labels(self):
+        return self._get_raw_labels().dtype == np.int64
+
+    @property
+    def label_shape(self):
+        if self._label_shape is None:
+            lab = self._get_raw_labels()
+            self._label_shape = [int(lab.max()) + 1] if lab.dtype == np.int64 else lab.shape[1:]
+        return list(self._label_shape)
+
+    @property
+    def label_dim(self):
+        shape = self.label_shape
+        assert len(shape) == 1
+        return shape[0]
+
+    @property
+    def has_labels(self):
+        return any(d != 0 for d in self.label_shape)
+
+    def get_label(self, idx):
+        lab = self._get_raw_labels()[self._raw_idx[idx]]
+        if lab.dtype != np.int64:
+            return lab.copy()
+        onehot = np.zeros(self.label_shape, dtype=np.float32)
+        onehot[lab] = 1
+        return onehot
+
+    def get_details(self, idx):
+        raw_idx = int(self._raw_idx[idx])
+        return dnnlib.EasyDict(raw_idx=raw_idx, xflip=bool(self._xflip[idx]), raw_label=self._get_raw_labels()[raw_idx].copy())
+
+    # -- items ----------------------------------------------------------------------------------------------------
     def __len__(self):
         return self._raw_idx.size
 
@@ -82,129 +123,79 @@ class Dataset(torch.utils.data.Dataset):
         assert isinstance(image, np.ndarray) and list(image.shape) == self.image_shape and image.dtype == self._dtype
         if self._xflip[idx]:
             assert image.ndim == 3
-            image = image[:, :, ::-1]
-        return image.copy(), self.get_label(idx), fname
+            image = image[:, :, ::-1]                       # mirrored left-right
+        return image.copy(), self.get_label(idx), fname      # .copy() makes the mirrored view contiguous
 
-    def get_label(self, idx):
-        label = self._get_raw_labels()[self._raw_idx[idx]]
-        if label.dtype == np.int64:
-            onehot = np.zeros(self.label_shape, dtype=np.float32)
-            onehot[label] = 1
-            label = onehot
-        return label.copy()
-
-    def get_details(self, idx):
-        d = dnnlib.EasyDict()
-        d.raw_idx = int(self._raw_idx[idx])
-        d.xflip = int(self._xflip[idx]) != 0
-        d.raw_label = self._get_raw_labels()[d.raw_idx].copy()
-        return d
-
+    # -- description ----------------------------------------------------------------------------------------------
     name = property(lambda self: self._name)
     dtype = property(lambda self: self._dtype)
-    modatilies = property(lambda self: self._modalities)      # (sic) the reference's spelling, :144
-    modalities = property(lambda self: self._modalities)
     split = property(lambda self: self._split)
+    modalities = property(lambda self: self._modalities)
+    modatilies = modalities                                  # (sic) the reference's spelling of the same property, :144
     image_shape = property(lambda self: list(self._raw_shape[1:]))
 
     @property
     def num_channels(self):
-        assert len(self.image_shape) == 3
-        return self.image_shape[0]
+        c, _, _ = self.image_shape
+        return c
 
     @property
     def resolution(self):
-        assert len(self.image_shape) == 3 and self.image_shape[1] == self.image_shape[2]
-        return self.image_shape[1]
-
-    @property
-    def label_shape(self):
-        if self._label_shape is None:
-            raw = self._get_raw_labels()
-            self._label_shape = [int(np.max(raw)) + 1] if raw.dtype == np.int64 else raw.shape[1:]
-        return list(self._label_shape)
-
-    @property
-    def label_dim(self):
-        assert len(self.label_shape) == 1
-        return self.label_shape[0]
-
-    @property
-    def has_labels(self):
-        return any(x != 0 for x in self.label_shape)
-
-    @property
-    def has_onehot_labels(self):
-        return self._get_raw_labels().dtype == np.int64
+        _, h, w = self.image_shape
+        assert h == w
+        return h
 
 
 class CustomImageFolderDataset(Dataset):
-    """Zip of `<split>/.../*.pickle` slices, each a dict {modality: HxW array}; channels = the requested modalities in order."""
+    """Zip of `<split>/.../*.pickle` slices, each a dict {modality: HxW array}; channels = the requested modalities in order; labels
+    from `<split>/dataset.json` = {"labels": [[path relative to <split>/, class | vector], ...]}."""
 
     def __init__(self, path, resolution=None, **super_kwargs):
-        self._path = path
-        self._zipfile = None
-        self._split = super_kwargs['split']
-        self._modalities = super_kwargs['modalities']
-        if self._file_ext(path) != '.zip':
+        if os.path.splitext(path)[1].lower() != '.zip':
             raise IOError('Path must point to a directory or zip')
-        self._type = 'zip'
-        self._all_fnames = set(self._get_zipfile().namelist())
-        self._image_fnames = sorted(f for f in self._all_fnames if self._file_ext(f) == '.pickle' and self._split in f)
-        if len(self._image_fnames) == 0:
+        self._path, self._type, self._zipfile = path, 'zip', None
+        self._split, self._modalities = super_kwargs['split'], super_kwargs['modalities']
+        self._all_fnames = set(self._zip().namelist())
+        self._image_fnames = sorted(f for f in self._all_fnames if f.lower().endswith('.pickle') and self._split in f)
+        if not self._image_fnames:
             raise IOError('No image files found in the specified path')
-        name = os.path.splitext(os.path.basename(path))[0]
-        raw_shape = [len(self._image_fnames)] + list(self._load_raw_image(0)[0].shape)
-        if resolution is not None and (raw_shape[2] != resolution or raw_shape[3] != resolution):
+        probe, _ = self._load_raw_image(0)
+        if resolution is not None and tuple(probe.shape[1:]) != (resolution, resolution):
             raise IOError('Image files do not match the specified resolution')
-        super().__init__(name=name, raw_shape=raw_shape, **super_kwargs)
+        super().__init__(name=os.path.splitext(os.path.basename(path))[0], raw_shape=[len(self._image_fnames), *probe.shape], **super_kwargs)
 
-    @staticmethod
-    def _file_ext(fname):
-        return os.path.splitext(fname)[1].lower()
-
-    def _get_zipfile(self):
+    def _zip(self):
         if self._zipfile is None:
-            self._zipfile = zipfile.ZipFile(self._path)
+            self._zipfile = zipfile.ZipFile(self._path)      # opened lazily so that every worker process gets its own handle
         return self._zipfile
 
-    def _open_file(self, fname):
-        return self._get_zipfile().open(fname, 'r')
-
     def close(self):
-        try:
-            if self._zipfile is not None:
-                self._zipfile.close()
-        finally:
-            self._zipfile = None
+        z, self._zipfile = self._zipfile, None
+        if z is not None:
+            z.close()
 
     def __getstate__(self):
         return dict(super().__getstate__(), _zipfile=None)
 
     def _load_raw_image(self, raw_idx):
         fname = self._image_fnames[raw_idx]
-        with self._open_file(fname) as f:
-            p = pickle.load(f)
+        with self._zip().open(fname, 'r') as f:
+            slices = pickle.load(f)
         assert len(self._modalities) > 0
-        first = p[self._modalities[0]]
-        out = np.zeros((len(self._modalities), first.shape[0], first.shape[1]), dtype=np.float32)
-        for i, m in enumerate(self._modalities):
-            out[i] = np.asarray(p[m]).astype('float32')
-        return out, fname
+        return np.stack([np.asarray(slices[m]).astype(np.float32) for m in self._modalities]), fname
 
     def _load_raw_labels(self):
-        fname = f'{self._split}/dataset.json'
-        if fname not in self._all_fnames:
+        meta = f'{self._split}/dataset.json'
+        if meta not in self._all_fnames:
             return None
-        with self._open_file(fname) as f:
-            labels = json.load(f)['labels']
-        if labels is None:
+        with self._zip().open(meta, 'r') as f:
+            table = json.load(f)['labels']
+        if table is None:
             return None
-        labels = dict(labels)
-        labels = [labels[os.path.relpath(f.replace('\\', '/'), f'{self._split}/')] for f in self._image_fnames]
-        assert len(labels) == len(self._image_fnames)
-        labels = np.array(labels)
-        return labels.astype({1: np.int64, 2: np.float32}[labels.ndim])
+        table = dict(table)
+        rows = np.array([table[os.path.relpath(f.replace('\\', '/'), f'{self._split}/')] for f in self._image_fnames])
+        assert len(rows) == len(self._image_fnames)
+        return rows.astype({1: np.int64, 2: np.float32}[rows.ndim])
 
 
 # ---------------------------------------------------------------------------------------------------------------------
