@@ -17,16 +17,85 @@ import torch
 from ..torch_utils import misc
 from ..torch_utils.ops import bias_act, conv2d_resample, fc, fma, modulated, rgb, upfirdn2d
 
+SQRT_HALF = np.sqrt(0.5)
+ARCHITECTURES = ('orig', 'skip', 'resnet')
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# small shared pieces
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _keep(module, **attrs):
+    """Plain (non-parameter) attributes of a layer, set in one place."""
+    for key, value in attrs.items():
+        setattr(module, key, value)
+
+
+def _layout(channels_last):
+    return torch.channels_last if channels_last else torch.contiguous_format
+
+
+def _working_type(use_fp16, channels_last, force_fp32):
+    """(dtype, memory_format) a block computes in: fp16 (+ channels-last) unless forced to fp32."""
+    half = use_fp16 and not force_fp32
+    return (torch.float16 if half else torch.float32), _layout(channels_last and not force_fp32)
+
+
+def _conv_weight(out_channels, in_channels, kernel_size, channels_last):
+    return torch.randn([out_channels, in_channels, kernel_size, kernel_size]).to(memory_format=_layout(channels_last))
+
+
+def _scaled(clamp, gain):
+    return None if clamp is None else clamp * gain
+
+
+def _describe(module, *names):
+    return ', '.join(f'{n}={getattr(module, n)}' for n in names)
+
+
+def _fp16_from(resolution_log2, num_fp16_res):
+    """Lowest resolution that runs in fp16: the top `num_fp16_res` resolutions, never below 8."""
+    return max(2 ** (resolution_log2 + 1 - num_fp16_res), 8)
+
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
     return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# modulated convolution
+# ---------------------------------------------------------------------------------------------------------------------
 
 # fused_modconv=True (eval-mode sampling: per-sample weights W * s * d and one grouped convolution, reference :79-89) is
 # evaluated on CUDA tensors as scale -> shared-weight convolution -> demodulate, which is the same function (4e-7 in fp32,
 # SURVEY A.3; pinned against the reference's own eval-mode output in tests/test_gpu_model.py) and keeps G_ema sampling on the
 # tcgen05 / fused element-wise kernels: 24.8 -> 3.9 ms per batch of 32 at 256x256 (tools/bench_sampling.py).  True restores the grouped convolution.
 grouped_fused_modconv = False
+
+
+def _demod_operands(x, weight, styles, shared_weight_route):
+    """(weight, styles, dcoefs) for a demodulated layer.  In fp16 both operands are pre-normalised by their infinity norms so
+    that neither the scaled activations nor the convolution overflow (demodulation makes the result invariant to it);
+    dcoefs[n,o] = rsqrt(sum_i s[n,i]^2 * sum_k W[o,i,k]^2 + eps), i.e. the reduction of the reference's [N,O,I,kh,kw] product
+    (:60-63) without materialising it."""
+    half = x.dtype == torch.float16
+    if shared_weight_route and modulated.prep_applicable(weight, styles):
+        # pre-normalisation and demodulation coefficients in four launches (csrc/modprep.cu) instead of ~13 tensor ops
+        w16, sn, dcoefs = modulated.prep(weight, styles, half)
+        return (w16, sn, dcoefs) if half else (weight, styles, dcoefs)
+    if half:
+        fan_in = weight.shape[1] * weight.shape[2] * weight.shape[3]
+        weight = weight * (1 / np.sqrt(fan_in) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+        styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
+    per_pair_energy = weight.square().sum(dim=[2, 3])                          # [O, I]
+    return weight, styles, (styles.square() @ per_pair_energy.t() + 1e-8).rsqrt()   # dcoefs [N, O]
+
+
+def _is_pixel_dot(x, weight, up, down, padding):
+    """ToRGB to one image channel on a channels-last CUDA tensor: a per-pixel dot product."""
+    out_channels, _, kh, kw = weight.shape
+    return (out_channels == 1 and kh == 1 and kw == 1 and up == 1 and down == 1 and padding == 0 and x.is_cuda and x.dim() == 4
+            and x.stride(1) == 1 and x.is_contiguous(memory_format=torch.channels_last))
 
 
 def modulated_conv2d(
@@ -42,194 +111,147 @@ def modulated_conv2d(
     bias_act_args=None,         # (not in the reference) dict(b, act, gain, clamp): apply the layer's bias_act here, so that on
                                 # channels-last CUDA tensors demodulation + noise + bias + activation run as one fused pass
 ):
-    batch_size = x.shape[0]
+    n = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
-    misc.assert_shape(weight, [out_channels, in_channels, kh, kw])
-    misc.assert_shape(x, [batch_size, in_channels, None, None])
-    misc.assert_shape(styles, [batch_size, in_channels])
-    if fused_modconv and x.is_cuda and not grouped_fused_modconv:
-        fused_modconv = False
-
-    # fp16: pre-normalise so that neither the scaled activations nor the conv overflow; demodulation makes the result
-    # invariant to both scalings.
+    misc.assert_shape(x, [n, in_channels, None, None])
+    misc.assert_shape(styles, [n, in_channels])
+    grouped = fused_modconv and not (x.is_cuda and not grouped_fused_modconv)
+    resample = dict(f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
     dcoefs = None
-    if demodulate and not fused_modconv and modulated.prep_applicable(weight, styles):
-        # pre-normalisation and demodulation coefficients in four launches (csrc/modprep.cu) instead of ~13 tensor ops
-        w16, sn, dcoefs = modulated.prep(weight, styles, x.dtype == torch.float16)
-        if x.dtype == torch.float16:
-            weight, styles = w16, sn
-    elif x.dtype == torch.float16 and demodulate:
-        weight = weight * (1 / np.sqrt(in_channels * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
-        styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
-
-    if demodulate and dcoefs is None:
-        # rsqrt(sum_i s[n,i]^2 * sum_k W[o,i,k]^2 + eps): identical to reducing the [N,O,I,kh,kw] product
-        # (reference :60-63) without materialising it.
-        wsq = weight.square().sum(dim=[2, 3])                                   # [O, I]
-        dcoefs = (styles.square() @ wsq.t() + 1e-8).rsqrt()                     # [N, O]
-
-    def finish(x):
-        if bias_act_args is None:
-            return x
-        return bias_act.bias_act(x, bias_act_args['b'], act=bias_act_args['act'], gain=bias_act_args['gain'], clamp=bias_act_args['clamp'])
-
-    if not fused_modconv:
-        if modulated.applicable(x):
-            x = modulated.mod_scale(x, styles)                                   # one pass forward, one pass backward (gx and gs)
-        else:
-            x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
-        if (out_channels == 1 and kh == 1 and kw == 1 and up == 1 and down == 1 and padding == 0 and x.is_cuda and x.dim() == 4
-                and x.stride(1) == 1 and x.is_contiguous(memory_format=torch.channels_last)):
-            # ToRGB to one image channel on a channels-last tensor is a per-pixel dot product: [N,H,W,C] @ [C,1] on a free view.
-            # Same rounding points as the 1x1 convolution (fp32 accumulation, one rounding of the result) and differentiable to
-            # any order by autograd -- this is the form the path-length pass uses; the library's convolution for Cout = 1 costs
-            # two fp32 kernels of 470 us plus format copies there.
-            x = torch.matmul(x.permute(0, 2, 3, 1), weight.to(x.dtype).reshape(in_channels, 1)).permute(0, 3, 1, 2)
-        else:
-            x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding, flip_weight=flip_weight)
-        if bias_act_args is not None and bias_act_args['act'] in ('linear', 'lrelu') and modulated.applicable(x):
-            spec = bias_act.activation_funcs[bias_act_args['act']]
-            gain = bias_act_args['gain'] if bias_act_args['gain'] is not None else spec.def_gain
-            return modulated.demod_act(x, dcoefs if demodulate else None, noise, bias_act_args['b'], act=bias_act_args['act'], alpha=spec.def_alpha,
-                                       gain=gain, clamp=bias_act_args['clamp'])
-        if demodulate and noise is not None:
-            x = fma.fma(x, dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1), noise.to(x.dtype))
-        elif demodulate:
-            x = x * dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1)
-        elif noise is not None:
-            x = x.add_(noise.to(x.dtype))
-        return finish(x)
-
-    # Fused: fold style (and demodulation) into per-sample weights, run as one grouped convolution.
-    w = weight.unsqueeze(0) * styles.reshape(batch_size, 1, -1, 1, 1)          # [N, O, I, kh, kw]
     if demodulate:
-        w = w * dcoefs.reshape(batch_size, -1, 1, 1, 1)
-    x = x.reshape(1, -1, *x.shape[2:])
-    w = w.reshape(-1, in_channels, kh, kw)
-    x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding, groups=batch_size, flip_weight=flip_weight)
-    x = x.reshape(batch_size, -1, *x.shape[2:])
-    if noise is not None:
-        x = x.add_(noise)
-    return finish(x)
+        weight, styles, dcoefs = _demod_operands(x, weight, styles, shared_weight_route=not grouped)
 
+    def epilogue(y):
+        if bias_act_args is None:
+            return y
+        return bias_act.bias_act(y, bias_act_args['b'], act=bias_act_args['act'], gain=bias_act_args['gain'], clamp=bias_act_args['clamp'])
+
+    if grouped:
+        # per-sample weights W * s (* d), one grouped convolution over the batch folded into the channel axis
+        per_sample = weight.unsqueeze(0) * styles.reshape(n, 1, -1, 1, 1)      # [N, O, I, kh, kw]
+        if demodulate:
+            per_sample = per_sample * dcoefs.reshape(n, -1, 1, 1, 1)
+        y = conv2d_resample.conv2d_resample(x=x.reshape(1, -1, *x.shape[2:]), w=per_sample.reshape(-1, in_channels, kh, kw).to(x.dtype), groups=n, **resample)
+        y = y.reshape(n, -1, *y.shape[2:])
+        return epilogue(y if noise is None else y.add_(noise))
+
+    # shared weight: scale the activations by the styles, convolve once, demodulate the result
+    fused_elementwise = modulated.applicable(x)
+    x = modulated.mod_scale(x, styles) if fused_elementwise else x * styles.to(x.dtype).reshape(n, -1, 1, 1)
+    if _is_pixel_dot(x, weight, up, down, padding):
+        # [N,H,W,C] @ [C,1] on a free view.  Same rounding points as the 1x1 convolution (fp32 accumulation, one rounding of the
+        # result) and differentiable to any order by autograd -- the form the path-length pass uses; the library's convolution
+        # for Cout = 1 costs two fp32 kernels of 470 us plus format copies there.
+        y = torch.matmul(x.permute(0, 2, 3, 1), weight.to(x.dtype).reshape(in_channels, 1)).permute(0, 3, 1, 2)
+    else:
+        y = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), **resample)
+    if bias_act_args is not None and bias_act_args['act'] in ('linear', 'lrelu') and modulated.applicable(y):
+        spec = bias_act.activation_funcs[bias_act_args['act']]
+        gain = spec.def_gain if bias_act_args['gain'] is None else bias_act_args['gain']
+        return modulated.demod_act(y, dcoefs, noise, bias_act_args['b'], act=bias_act_args['act'], alpha=spec.def_alpha, gain=gain,
+                                   clamp=bias_act_args['clamp'])
+    if dcoefs is not None:
+        d = dcoefs.to(y.dtype).reshape(n, -1, 1, 1)
+        y = y * d if noise is None else fma.fma(y, d, noise.to(y.dtype))
+    elif noise is not None:
+        y = y.add_(noise.to(y.dtype))
+    return epilogue(y)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# layers
+# ---------------------------------------------------------------------------------------------------------------------
 
 class FullyConnectedLayer(torch.nn.Module):
     def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0):
         super().__init__()
-        self.in_features = in_features
-        self.out_features = out_features
-        self.activation = activation
+        _keep(self, in_features=in_features, out_features=out_features, activation=activation,
+              weight_gain=lr_multiplier / np.sqrt(in_features), bias_gain=lr_multiplier)
         self.weight = torch.nn.Parameter(torch.randn([out_features, in_features]) / lr_multiplier)
         self.bias = torch.nn.Parameter(torch.full([out_features], np.float32(bias_init))) if bias else None
-        self.weight_gain = lr_multiplier / np.sqrt(in_features)
-        self.bias_gain = lr_multiplier
 
     def forward(self, x):
+        linear = self.activation == 'linear'
         if fc.applicable(x, self.weight):
             # one kernel for gains + GEMM + bias (csrc/fc.cu); the activation of non-linear layers stays with bias_act
             y = fc.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain)
-            if self.activation == 'linear':
-                return y
-            return bias_act.bias_act(y, None, act=self.activation)
+            return y if linear else bias_act.bias_act(y, None, act=self.activation)
         w = self.weight.to(x.dtype) * self.weight_gain
-        b = self.bias
-        if b is not None:
-            b = b.to(x.dtype)
-            if self.bias_gain != 1:
-                b = b * self.bias_gain
-        if self.activation == 'linear' and b is not None:
+        b = None
+        if self.bias is not None:
+            b = self.bias.to(x.dtype)
+            b = b if self.bias_gain == 1 else b * self.bias_gain
+        if linear and b is not None:
             return torch.addmm(b.unsqueeze(0), x, w.t())
-        x = x.matmul(w.t())
-        return bias_act.bias_act(x, b, act=self.activation)
+        return bias_act.bias_act(x.matmul(w.t()), b, act=self.activation)
 
     def extra_repr(self):
-        return f'in_features={self.in_features:d}, out_features={self.out_features:d}, activation={self.activation:s}'
+        return _describe(self, 'in_features', 'out_features', 'activation')
 
 
 class Conv2dLayer(torch.nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1,
                  resample_filter=[1, 3, 3, 1], conv_clamp=None, channels_last=False, trainable=True):
         super().__init__()
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.activation = activation
-        self.up = up
-        self.down = down
-        self.conv_clamp = conv_clamp
+        _keep(self, in_channels=in_channels, out_channels=out_channels, activation=activation, up=up, down=down, conv_clamp=conv_clamp,
+              padding=kernel_size // 2, weight_gain=1 / np.sqrt(in_channels * kernel_size * kernel_size),
+              act_gain=bias_act.activation_funcs[activation].def_gain)
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
-        self.padding = kernel_size // 2
-        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
-        self.act_gain = bias_act.activation_funcs[activation].def_gain
-        memory_format = torch.channels_last if channels_last else torch.contiguous_format
-        weight = torch.randn([out_channels, in_channels, kernel_size, kernel_size]).to(memory_format=memory_format)
-        bias = torch.zeros([out_channels]) if bias else None
-        if trainable:
-            self.weight = torch.nn.Parameter(weight)
-            self.bias = torch.nn.Parameter(bias) if bias is not None else None
-        else:
-            self.register_buffer('weight', weight)
-            if bias is not None:
-                self.register_buffer('bias', bias)
+        tensors = dict(weight=_conv_weight(out_channels, in_channels, kernel_size, channels_last), bias=torch.zeros([out_channels]) if bias else None)
+        for name, value in tensors.items():                  # frozen layers (freeze_layers of the discriminator) keep them as buffers
+            if value is None:
+                setattr(self, name, None)
+            elif trainable:
+                setattr(self, name, torch.nn.Parameter(value))
             else:
-                self.bias = None
+                self.register_buffer(name, value)
 
     def forward(self, x, gain=1):
-        w = self.weight * self.weight_gain
-        b = self.bias.to(x.dtype) if self.bias is not None else None
-        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        if (self.in_channels == 1 and self.weight.shape[2] == 1 and self.up == 1 and self.down == 1 and self.activation in ('linear', 'lrelu')
-                and rgb.applicable(x, self.out_channels)):
+        w = (self.weight * self.weight_gain).to(x.dtype)
+        b = None if self.bias is None else self.bias.to(x.dtype)
+        act = dict(act=self.activation, gain=self.act_gain * gain, clamp=_scaled(self.conv_clamp, gain))
+        simple_act = self.activation in ('linear', 'lrelu')
+        plain = self.up == 1 and self.down == 1
+        if simple_act and plain and self.in_channels == 1 and self.weight.shape[2] == 1 and rgb.applicable(x, self.out_channels):
             # FromRGB on single-channel slices: outer product + bias_act in one pass, written channels-last (csrc/rgb.cu)
-            y = rgb.fromrgb1(x, w.to(x.dtype).reshape(-1), b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
-            return y
-        if self.up == 1 and x.is_cuda and self.activation in ('linear', 'lrelu'):
+            return rgb.fromrgb1(x, w.reshape(-1), b, **act)
+        resample = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding)
+        if simple_act and self.up == 1 and x.is_cuda:
             # the convolution is the last kernel of conv2d_resample: its bias_act rides in the convolution's epilogue
-            return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,
-                                                   flip_weight=True, epilogue=dict(b=b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp))
-        x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
-                                            padding=self.padding, flip_weight=(self.up == 1))
-        return bias_act.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
+            return conv2d_resample.conv2d_resample(x=x, w=w, flip_weight=True, epilogue=dict(b=b, **act), **resample)
+        y = conv2d_resample.conv2d_resample(x=x, w=w, flip_weight=(self.up == 1), **resample)
+        return bias_act.bias_act(y, b, **act)
 
     def extra_repr(self):
-        return (f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, activation={self.activation:s}, '
-                f'up={self.up}, down={self.down}')
+        return _describe(self, 'in_channels', 'out_channels', 'activation', 'up', 'down')
 
 
 class MappingNetwork(torch.nn.Module):
     def __init__(self, z_dim, c_dim, w_dim, num_ws, num_layers=8, embed_features=None, layer_features=None, activation='lrelu',
                  lr_multiplier=0.01, w_avg_beta=0.998):
         super().__init__()
-        self.z_dim = z_dim
-        self.c_dim = c_dim
-        self.w_dim = w_dim
-        self.num_ws = num_ws
-        self.num_layers = num_layers
-        self.w_avg_beta = w_avg_beta
-        if embed_features is None:
-            embed_features = w_dim
-        if c_dim == 0:
-            embed_features = 0
-        if layer_features is None:
-            layer_features = w_dim
-        features = [z_dim + embed_features] + [layer_features] * (num_layers - 1) + [w_dim]
+        _keep(self, z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=num_ws, num_layers=num_layers, w_avg_beta=w_avg_beta)
+        embed_features = 0 if c_dim == 0 else (w_dim if embed_features is None else embed_features)
+        hidden = w_dim if layer_features is None else layer_features
+        widths = [z_dim + embed_features, *([hidden] * (num_layers - 1)), w_dim]
         if c_dim > 0:
             self.embed = FullyConnectedLayer(c_dim, embed_features)
-        for idx in range(num_layers):
-            setattr(self, f'fc{idx}', FullyConnectedLayer(features[idx], features[idx + 1], activation=activation, lr_multiplier=lr_multiplier))
+        for idx, (fan_in, fan_out) in enumerate(zip(widths[:-1], widths[1:])):
+            setattr(self, f'fc{idx}', FullyConnectedLayer(fan_in, fan_out, activation=activation, lr_multiplier=lr_multiplier))
         if num_ws is not None and w_avg_beta is not None:
             self.register_buffer('w_avg', torch.zeros([w_dim]))
 
     def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False, ema_rows=None):
         # ema_rows (not in the reference): only the first `ema_rows` rows feed the w_avg update -- lets a caller map two latent
         # batches in one pass while tracking the average of the first, as two separate calls would
-        x = None
+        parts = []
         if self.z_dim > 0:
             misc.assert_shape(z, [None, self.z_dim])
-            x = normalize_2nd_moment(z.to(torch.float32))
+            parts.append(normalize_2nd_moment(z.to(torch.float32)))
         if self.c_dim > 0:
             misc.assert_shape(c, [None, self.c_dim])
-            y = normalize_2nd_moment(self.embed(c.to(torch.float32)))
-            x = torch.cat([x, y], dim=1) if x is not None else y
+            parts.append(normalize_2nd_moment(self.embed(c.to(torch.float32))))
+        x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         for idx in range(self.num_layers):
             x = getattr(self, f'fc{idx}')(x)
         if update_emas and self.w_avg_beta is not None:
@@ -245,177 +267,147 @@ class MappingNetwork(torch.nn.Module):
         return x
 
     def extra_repr(self):
-        return f'z_dim={self.z_dim:d}, c_dim={self.c_dim:d}, w_dim={self.w_dim:d}, num_ws={self.num_ws}'
+        return _describe(self, 'z_dim', 'c_dim', 'w_dim', 'num_ws')
 
 
 class SynthesisLayer(torch.nn.Module):
     def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, use_noise=True, activation='lrelu',
                  resample_filter=[1, 3, 3, 1], conv_clamp=None, channels_last=False):
         super().__init__()
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.w_dim = w_dim
-        self.resolution = resolution
-        self.up = up
-        self.use_noise = use_noise
-        self.activation = activation
-        self.conv_clamp = conv_clamp
+        _keep(self, in_channels=in_channels, out_channels=out_channels, w_dim=w_dim, resolution=resolution, up=up, use_noise=use_noise,
+              activation=activation, conv_clamp=conv_clamp, padding=kernel_size // 2, act_gain=bias_act.activation_funcs[activation].def_gain)
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
-        self.padding = kernel_size // 2
-        self.act_gain = bias_act.activation_funcs[activation].def_gain
         self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
-        memory_format = torch.channels_last if channels_last else torch.contiguous_format
-        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]).to(memory_format=memory_format))
+        self.weight = torch.nn.Parameter(_conv_weight(out_channels, in_channels, kernel_size, channels_last))
         if use_noise:
             self.register_buffer('noise_const', torch.randn([resolution, resolution]))
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
+    def _noise(self, x, noise_mode):
+        if not self.use_noise or noise_mode == 'none':
+            return None
+        if noise_mode == 'const':
+            return self.noise_const * self.noise_strength
+        return torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
+
     def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
         assert noise_mode in ['random', 'const', 'none']
-        in_resolution = self.resolution // self.up
-        misc.assert_shape(x, [None, self.in_channels, in_resolution, in_resolution])
+        side = self.resolution // self.up
+        misc.assert_shape(x, [None, self.in_channels, side, side])
         styles = self.affine(w)
-        noise = None
-        if self.use_noise and noise_mode == 'random':
-            noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
-        if self.use_noise and noise_mode == 'const':
-            noise = self.noise_const * self.noise_strength
-        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        noise = self._noise(x, noise_mode)
+        act = dict(b=self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=_scaled(self.conv_clamp, gain))
         return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                                resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
-                                bias_act_args=dict(b=self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp))
+                                resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv, bias_act_args=act)
 
     def extra_repr(self):
-        return (f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, w_dim={self.w_dim:d}, '
-                f'resolution={self.resolution:d}, up={self.up}, activation={self.activation:s}')
+        return _describe(self, 'in_channels', 'out_channels', 'w_dim', 'resolution', 'up', 'activation')
 
 
 class ToRGBLayer(torch.nn.Module):
     def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, conv_clamp=None, channels_last=False):
         super().__init__()
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.w_dim = w_dim
-        self.conv_clamp = conv_clamp
+        _keep(self, in_channels=in_channels, out_channels=out_channels, w_dim=w_dim, conv_clamp=conv_clamp,
+              weight_gain=1 / np.sqrt(in_channels * kernel_size * kernel_size))
         self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
-        memory_format = torch.channels_last if channels_last else torch.contiguous_format
-        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]).to(memory_format=memory_format))
+        self.weight = torch.nn.Parameter(_conv_weight(out_channels, in_channels, kernel_size, channels_last))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
-        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        if (not fused_modconv) and self.weight.shape[2] == 1 and rgb.torgb_applicable(x, self.out_channels):
+        if not fused_modconv and self.weight.shape[2] == 1 and rgb.torgb_applicable(x, self.out_channels):
             # single-channel slices: modulation + 1x1 convolution + bias + clamp in one pass over x (csrc/rgb.cu)
             return rgb.torgb1(x, self.weight, styles, self.bias, clamp=self.conv_clamp)
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-        return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
+        y = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+        return bias_act.bias_act(y, self.bias.to(y.dtype), clamp=self.conv_clamp)
 
     def extra_repr(self):
-        return f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, w_dim={self.w_dim:d}'
+        return _describe(self, 'in_channels', 'out_channels', 'w_dim')
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generator
+# ---------------------------------------------------------------------------------------------------------------------
 
 class SynthesisBlock(torch.nn.Module):
     def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, architecture='skip',
                  resample_filter=[1, 3, 3, 1], conv_clamp=256, use_fp16=False, fp16_channels_last=True,
                  fused_modconv_default=True, **layer_kwargs):
-        assert architecture in ['orig', 'skip', 'resnet']
+        assert architecture in ARCHITECTURES
         super().__init__()
-        self.in_channels = in_channels
-        self.w_dim = w_dim
-        self.resolution = resolution
-        self.img_channels = img_channels
-        self.is_last = is_last
-        self.architecture = architecture
-        self.use_fp16 = use_fp16
-        self.channels_last = (use_fp16 and fp16_channels_last)
-        self.fused_modconv_default = fused_modconv_default
+        first = in_channels == 0                             # the 4x4 block starts from a learned constant
+        has_torgb = is_last or architecture == 'skip'
+        _keep(self, in_channels=in_channels, w_dim=w_dim, resolution=resolution, img_channels=img_channels, is_last=is_last,
+              architecture=architecture, use_fp16=use_fp16, channels_last=(use_fp16 and fp16_channels_last),
+              fused_modconv_default=fused_modconv_default, num_conv=1 if first else 2, num_torgb=int(has_torgb))
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
-        self.num_conv = 0
-        self.num_torgb = 0
-        if in_channels == 0:
+        layer = dict(w_dim=w_dim, conv_clamp=conv_clamp, channels_last=self.channels_last)
+        if first:
             self.const = torch.nn.Parameter(torch.randn([out_channels, resolution, resolution]))
-        if in_channels != 0:
-            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2, resample_filter=resample_filter,
-                                        conv_clamp=conv_clamp, channels_last=self.channels_last, **layer_kwargs)
-            self.num_conv += 1
-        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp,
-                                    channels_last=self.channels_last, **layer_kwargs)
-        self.num_conv += 1
-        if is_last or architecture == 'skip':
-            self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, channels_last=self.channels_last)
-            self.num_torgb += 1
-        if in_channels != 0 and architecture == 'resnet':
+        else:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, resolution=resolution, up=2, resample_filter=resample_filter, **layer, **layer_kwargs)
+        self.conv1 = SynthesisLayer(out_channels, out_channels, resolution=resolution, **layer, **layer_kwargs)
+        if has_torgb:
+            self.torgb = ToRGBLayer(out_channels, img_channels, **layer)
+        if not first and architecture == 'resnet':
             self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=2, resample_filter=resample_filter,
                                     channels_last=self.channels_last)
 
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, **layer_kwargs):
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
-        w_iter = iter(ws.unbind(dim=1))
-        if ws.device.type != 'cuda':
-            force_fp32 = True
-        dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
-        memory_format = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
-        if fused_modconv is None:
-            fused_modconv = self.fused_modconv_default
-        if fused_modconv == 'inference_only':
-            fused_modconv = (not self.training)
+        styles = iter(ws.unbind(dim=1))
+        dtype, memory_format = _working_type(self.use_fp16, self.channels_last, force_fp32 or ws.device.type != 'cuda')
+        fused = self.fused_modconv_default if fused_modconv is None else fused_modconv
+        if fused == 'inference_only':
+            fused = not self.training
+        half_res = self.resolution // 2
+        conv = dict(fused_modconv=fused, **layer_kwargs)
 
         if self.in_channels == 0:
-            x = self.const.to(dtype=dtype, memory_format=memory_format)
-            x = x.unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
+            x = self.const.to(dtype=dtype, memory_format=memory_format).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
+            x = self.conv1(x, next(styles), **conv)
         else:
-            misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
+            misc.assert_shape(x, [None, self.in_channels, half_res, half_res])
             x = x.to(dtype=dtype, memory_format=memory_format)
-
-        if self.in_channels == 0:
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-        elif self.architecture == 'resnet':
-            y = self.skip(x, gain=np.sqrt(0.5))
-            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, gain=np.sqrt(0.5), **layer_kwargs)
-            x = y.add_(x)
-        else:
-            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            if self.architecture == 'resnet':
+                shortcut = self.skip(x, gain=SQRT_HALF)
+                x = self.conv0(x, next(styles), **conv)
+                x = self.conv1(x, next(styles), gain=SQRT_HALF, **conv)
+                x = shortcut.add_(x)
+            else:
+                x = self.conv0(x, next(styles), **conv)
+                x = self.conv1(x, next(styles), **conv)
 
         if img is not None:
-            misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
+            misc.assert_shape(img, [None, self.img_channels, half_res, half_res])
             img = upfirdn2d.upsample2d(img, self.resample_filter)
-        if self.is_last or self.architecture == 'skip':
-            y = self.torgb(x, next(w_iter), fused_modconv=fused_modconv)
-            y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
-            img = img.add_(y) if img is not None else y
+        if self.num_torgb:
+            rgb_out = self.torgb(x, next(styles), fused_modconv=fused).to(dtype=torch.float32, memory_format=torch.contiguous_format)
+            img = rgb_out if img is None else img.add_(rgb_out)
 
-        assert x.dtype == dtype
-        assert img is None or img.dtype == torch.float32
+        assert x.dtype == dtype and (img is None or img.dtype == torch.float32)
         return x, img
 
     def extra_repr(self):
-        return f'resolution={self.resolution:d}, architecture={self.architecture:s}'
+        return _describe(self, 'resolution', 'architecture')
 
 
 class SynthesisNetwork(torch.nn.Module):
     def __init__(self, w_dim, img_resolution, img_channels, channel_base=32768, channel_max=512, num_fp16_res=4, **block_kwargs):
         assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
         super().__init__()
-        self.w_dim = w_dim
-        self.img_resolution = img_resolution
-        self.img_resolution_log2 = int(np.log2(img_resolution))
-        self.img_channels = img_channels
-        self.num_fp16_res = num_fp16_res
-        self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
-        channels = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
-        fp16_resolution = max(2 ** (self.img_resolution_log2 + 1 - num_fp16_res), 8)
-        self.num_ws = 0
+        log2 = int(np.log2(img_resolution))
+        _keep(self, w_dim=w_dim, img_resolution=img_resolution, img_resolution_log2=log2, img_channels=img_channels, num_fp16_res=num_fp16_res,
+              block_resolutions=[2 ** i for i in range(2, log2 + 1)], num_ws=0)
+        width = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        first_fp16 = _fp16_from(log2, num_fp16_res)
         for res in self.block_resolutions:
-            in_channels = channels[res // 2] if res > 4 else 0
-            block = SynthesisBlock(in_channels, channels[res], w_dim=w_dim, resolution=res, img_channels=img_channels,
-                                   is_last=(res == self.img_resolution), use_fp16=(res >= fp16_resolution), **block_kwargs)
-            self.num_ws += block.num_conv
-            if res == self.img_resolution:
-                self.num_ws += block.num_torgb
+            last = res == img_resolution
+            block = SynthesisBlock(width[res // 2] if res > 4 else 0, width[res], w_dim=w_dim, resolution=res, img_channels=img_channels,
+                                   is_last=last, use_fp16=(res >= first_fp16), **block_kwargs)
+            # every conv has its own w; a block's ToRGB shares the next block's first w, so only the last one adds to the count
+            self.num_ws += block.num_conv + (block.num_torgb if last else 0)
             setattr(self, f'b{res}', block)
 
     def forward(self, ws, **block_kwargs):
@@ -425,30 +417,22 @@ class SynthesisNetwork(torch.nn.Module):
             # one [num_ws, N, w_dim] copy, handed to the blocks as [N, n, w_dim] views whose per-layer slices are contiguous rows:
             # the style affines read them in place instead of 20 per-layer .contiguous() copies (same values)
             ws = ws.transpose(0, 1).contiguous().transpose(0, 1)
-        block_ws = []
-        w_idx = 0
+        x = img = None
+        start = 0
         for res in self.block_resolutions:
             block = getattr(self, f'b{res}')
-            block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
-            w_idx += block.num_conv
-        x = img = None
-        for res, cur_ws in zip(self.block_resolutions, block_ws):
-            x, img = getattr(self, f'b{res}')(x, img, cur_ws, **block_kwargs)
+            x, img = block(x, img, ws.narrow(1, start, block.num_conv + block.num_torgb), **block_kwargs)
+            start += block.num_conv
         return img
 
     def extra_repr(self):
-        return (f'w_dim={self.w_dim:d}, num_ws={self.num_ws:d}, img_resolution={self.img_resolution:d}, '
-                f'img_channels={self.img_channels:d}, num_fp16_res={self.num_fp16_res:d}')
+        return _describe(self, 'w_dim', 'num_ws', 'img_resolution', 'img_channels', 'num_fp16_res')
 
 
 class Generator(torch.nn.Module):
     def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, **synthesis_kwargs):
         super().__init__()
-        self.z_dim = z_dim
-        self.c_dim = c_dim
-        self.w_dim = w_dim
-        self.img_resolution = img_resolution
-        self.img_channels = img_channels
+        _keep(self, z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels)
         self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
         self.num_ws = self.synthesis.num_ws
         self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
@@ -458,157 +442,134 @@ class Generator(torch.nn.Module):
         return self.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# discriminator
+# ---------------------------------------------------------------------------------------------------------------------
+
 class DiscriminatorBlock(torch.nn.Module):
     def __init__(self, in_channels, tmp_channels, out_channels, resolution, img_channels, first_layer_idx, architecture='resnet',
                  activation='lrelu', resample_filter=[1, 3, 3, 1], conv_clamp=None, use_fp16=False, fp16_channels_last=True,
                  freeze_layers=0):
-        assert in_channels in [0, tmp_channels]
-        assert architecture in ['orig', 'skip', 'resnet']
+        assert in_channels in [0, tmp_channels] and architecture in ARCHITECTURES
         super().__init__()
-        self.in_channels = in_channels
-        self.resolution = resolution
-        self.img_channels = img_channels
-        self.first_layer_idx = first_layer_idx
-        self.architecture = architecture
-        self.use_fp16 = use_fp16
-        self.channels_last = (use_fp16 and fp16_channels_last)
+        _keep(self, in_channels=in_channels, resolution=resolution, img_channels=img_channels, first_layer_idx=first_layer_idx,
+              architecture=architecture, use_fp16=use_fp16, channels_last=(use_fp16 and fp16_channels_last), num_layers=0)
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
-        self.num_layers = 0
 
-        def next_trainable():
-            trainable = (self.first_layer_idx + self.num_layers >= freeze_layers)
+        def add(name, cin, cout, kernel_size, **kw):
+            """Layers are numbered across the whole discriminator; the first `freeze_layers` of them are not trained."""
+            trainable = first_layer_idx + self.num_layers >= freeze_layers
             self.num_layers += 1
-            return trainable
+            setattr(self, name, Conv2dLayer(cin, cout, kernel_size=kernel_size, trainable=trainable, channels_last=self.channels_last, **kw))
 
         if in_channels == 0 or architecture == 'skip':
-            self.fromrgb = Conv2dLayer(img_channels, tmp_channels, kernel_size=1, activation=activation, trainable=next_trainable(),
-                                       conv_clamp=conv_clamp, channels_last=self.channels_last)
-        self.conv0 = Conv2dLayer(tmp_channels, tmp_channels, kernel_size=3, activation=activation, trainable=next_trainable(),
-                                 conv_clamp=conv_clamp, channels_last=self.channels_last)
-        self.conv1 = Conv2dLayer(tmp_channels, out_channels, kernel_size=3, activation=activation, down=2, trainable=next_trainable(),
-                                 resample_filter=resample_filter, conv_clamp=conv_clamp, channels_last=self.channels_last)
+            add('fromrgb', img_channels, tmp_channels, 1, activation=activation, conv_clamp=conv_clamp)
+        add('conv0', tmp_channels, tmp_channels, 3, activation=activation, conv_clamp=conv_clamp)
+        add('conv1', tmp_channels, out_channels, 3, activation=activation, down=2, resample_filter=resample_filter, conv_clamp=conv_clamp)
         if architecture == 'resnet':
-            self.skip = Conv2dLayer(tmp_channels, out_channels, kernel_size=1, bias=False, down=2, trainable=next_trainable(),
-                                    resample_filter=resample_filter, channels_last=self.channels_last)
+            add('skip', tmp_channels, out_channels, 1, bias=False, down=2, resample_filter=resample_filter)
 
     def forward(self, x, img, force_fp32=False):
-        if (x if x is not None else img).device.type != 'cuda':
-            force_fp32 = True
-        dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
-        memory_format = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
+        on_cuda = (img if x is None else x).device.type == 'cuda'
+        dtype, memory_format = _working_type(self.use_fp16, self.channels_last, force_fp32 or not on_cuda)
+        square = [self.resolution, self.resolution]
         if x is not None:
-            misc.assert_shape(x, [None, self.in_channels, self.resolution, self.resolution])
+            misc.assert_shape(x, [None, self.in_channels, *square])
             x = x.to(dtype=dtype, memory_format=memory_format)
         if self.in_channels == 0 or self.architecture == 'skip':
-            misc.assert_shape(img, [None, self.img_channels, self.resolution, self.resolution])
+            misc.assert_shape(img, [None, self.img_channels, *square])
             img = img.to(dtype=dtype, memory_format=memory_format)
-            y = self.fromrgb(img)
-            x = x + y if x is not None else y
+            features = self.fromrgb(img)
+            x = features if x is None else x + features
             img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
         if self.architecture == 'resnet':
-            y = self.skip(x, gain=np.sqrt(0.5))
-            x = self.conv0(x)
-            x = self.conv1(x, gain=np.sqrt(0.5))
-            x = y.add_(x)
+            shortcut = self.skip(x, gain=SQRT_HALF)
+            x = self.conv1(self.conv0(x), gain=SQRT_HALF)
+            x = shortcut.add_(x)
         else:
-            x = self.conv0(x)
-            x = self.conv1(x)
+            x = self.conv1(self.conv0(x))
         assert x.dtype == dtype
         return x, img
 
     def extra_repr(self):
-        return f'resolution={self.resolution:d}, architecture={self.architecture:s}'
+        return _describe(self, 'resolution', 'architecture')
 
 
 class MinibatchStdLayer(torch.nn.Module):
     def __init__(self, group_size, num_channels=1):
         super().__init__()
-        self.group_size = group_size
-        self.num_channels = num_channels
+        _keep(self, group_size=group_size, num_channels=num_channels)
 
     def forward(self, x):
-        N, C, H, W = x.shape
-        G = min(int(self.group_size), int(N)) if self.group_size is not None else int(N)
-        F = self.num_channels
-        c = C // F
-        y = x.reshape(G, -1, F, c, H, W)        # [G n F c H W]: minibatch split into n groups of G, channels into F groups of c
-        y = y - y.mean(dim=0)
-        y = y.square().mean(dim=0)              # variance over the group
-        y = (y + 1e-8).sqrt()
-        y = y.mean(dim=[2, 3, 4])               # [n F]
-        y = y.reshape(-1, F, 1, 1).repeat(G, 1, H, W)
-        return torch.cat([x, y], dim=1)
+        n, channels, h, w = x.shape
+        group = int(n) if self.group_size is None else min(int(self.group_size), int(n))
+        stats = self.num_channels
+        # [G, n/G, F, C/F, H, W]: member g of group j is sample g * (n/G) + j; channels in F sets
+        members = x.reshape(group, -1, stats, channels // stats, h, w)
+        spread = (members - members.mean(dim=0)).square().mean(dim=0)       # variance over the group's members
+        per_group = (spread + 1e-8).sqrt().mean(dim=[2, 3, 4])               # [n/G, F]
+        plane = per_group.reshape(-1, stats, 1, 1).repeat(group, 1, h, w)
+        return torch.cat([x, plane], dim=1)
 
     def extra_repr(self):
-        return f'group_size={self.group_size}, num_channels={self.num_channels:d}'
+        return _describe(self, 'group_size', 'num_channels')
 
 
 class DiscriminatorEpilogue(torch.nn.Module):
     def __init__(self, in_channels, cmap_dim, resolution, img_channels, architecture='resnet', mbstd_group_size=4,
                  mbstd_num_channels=1, activation='lrelu', conv_clamp=None):
-        assert architecture in ['orig', 'skip', 'resnet']
+        assert architecture in ARCHITECTURES
         super().__init__()
-        self.in_channels = in_channels
-        self.cmap_dim = cmap_dim
-        self.resolution = resolution
-        self.img_channels = img_channels
-        self.architecture = architecture
+        _keep(self, in_channels=in_channels, cmap_dim=cmap_dim, resolution=resolution, img_channels=img_channels, architecture=architecture)
         if architecture == 'skip':
             self.fromrgb = Conv2dLayer(img_channels, in_channels, kernel_size=1, activation=activation)
         self.mbstd = MinibatchStdLayer(group_size=mbstd_group_size, num_channels=mbstd_num_channels) if mbstd_num_channels > 0 else None
         self.conv = Conv2dLayer(in_channels + mbstd_num_channels, in_channels, kernel_size=3, activation=activation, conv_clamp=conv_clamp)
-        self.fc = FullyConnectedLayer(in_channels * (resolution ** 2), in_channels, activation=activation)
-        self.out = FullyConnectedLayer(in_channels, 1 if cmap_dim == 0 else cmap_dim)
+        self.fc = FullyConnectedLayer(in_channels * resolution * resolution, in_channels, activation=activation)
+        self.out = FullyConnectedLayer(in_channels, cmap_dim if cmap_dim > 0 else 1)
 
     def forward(self, x, img, cmap, force_fp32=False):
-        misc.assert_shape(x, [None, self.in_channels, self.resolution, self.resolution])
-        dtype = torch.float32
-        x = x.to(dtype=dtype, memory_format=torch.contiguous_format)
+        square = [self.resolution, self.resolution]
+        misc.assert_shape(x, [None, self.in_channels, *square])
+        fp32 = dict(dtype=torch.float32, memory_format=torch.contiguous_format)
+        x = x.to(**fp32)
         if self.architecture == 'skip':
-            misc.assert_shape(img, [None, self.img_channels, self.resolution, self.resolution])
-            img = img.to(dtype=dtype, memory_format=torch.contiguous_format)
-            x = x + self.fromrgb(img)
+            misc.assert_shape(img, [None, self.img_channels, *square])
+            x = x + self.fromrgb(img.to(**fp32))
         if self.mbstd is not None:
             x = self.mbstd(x)
-        x = self.conv(x)
-        x = self.fc(x.flatten(1))
-        x = self.out(x)
+        logits = self.out(self.fc(self.conv(x).flatten(1)))
         if self.cmap_dim > 0:
+            # projection discriminator: score = <features, embedding of the class> / sqrt(dim)
             misc.assert_shape(cmap, [None, self.cmap_dim])
-            x = (x * cmap).sum(dim=1, keepdim=True) * (1 / np.sqrt(self.cmap_dim))
-        assert x.dtype == dtype
-        return x
+            logits = (logits * cmap).sum(dim=1, keepdim=True) * (1 / np.sqrt(self.cmap_dim))
+        assert logits.dtype == torch.float32
+        return logits
 
     def extra_repr(self):
-        return f'resolution={self.resolution:d}, architecture={self.architecture:s}'
+        return _describe(self, 'resolution', 'architecture')
 
 
 class Discriminator(torch.nn.Module):
     def __init__(self, c_dim, img_resolution, img_channels, architecture='resnet', channel_base=32768, channel_max=512,
                  num_fp16_res=4, conv_clamp=256, cmap_dim=None, block_kwargs={}, mapping_kwargs={}, epilogue_kwargs={}):
         super().__init__()
-        self.c_dim = c_dim
-        self.img_resolution = img_resolution
-        self.img_resolution_log2 = int(np.log2(img_resolution))
-        self.img_channels = img_channels
-        self.block_resolutions = [2 ** i for i in range(self.img_resolution_log2, 2, -1)]
-        channels = {res: min(channel_base // res, channel_max) for res in self.block_resolutions + [4]}
-        fp16_resolution = max(2 ** (self.img_resolution_log2 + 1 - num_fp16_res), 8)
-        if cmap_dim is None:
-            cmap_dim = channels[4]
-        if c_dim == 0:
-            cmap_dim = 0
-        common = dict(img_channels=img_channels, architecture=architecture, conv_clamp=conv_clamp)
-        cur_layer_idx = 0
+        log2 = int(np.log2(img_resolution))
+        _keep(self, c_dim=c_dim, img_resolution=img_resolution, img_resolution_log2=log2, img_channels=img_channels,
+              block_resolutions=[2 ** i for i in range(log2, 2, -1)])
+        width = {res: min(channel_base // res, channel_max) for res in [*self.block_resolutions, 4]}
+        first_fp16 = _fp16_from(log2, num_fp16_res)
+        cmap_dim = 0 if c_dim == 0 else (width[4] if cmap_dim is None else cmap_dim)
+        shared = dict(img_channels=img_channels, architecture=architecture, conv_clamp=conv_clamp)
+        layers_so_far = 0
         for res in self.block_resolutions:
-            in_channels = channels[res] if res < img_resolution else 0
-            block = DiscriminatorBlock(in_channels, channels[res], channels[res // 2], resolution=res, first_layer_idx=cur_layer_idx,
-                                       use_fp16=(res >= fp16_resolution), **block_kwargs, **common)
+            block = DiscriminatorBlock(width[res] if res < img_resolution else 0, width[res], width[res // 2], resolution=res,
+                                       first_layer_idx=layers_so_far, use_fp16=(res >= first_fp16), **block_kwargs, **shared)
             setattr(self, f'b{res}', block)
-            cur_layer_idx += block.num_layers
+            layers_so_far += block.num_layers
         if c_dim > 0:
             self.mapping = MappingNetwork(z_dim=0, c_dim=c_dim, w_dim=cmap_dim, num_ws=None, w_avg_beta=None, **mapping_kwargs)
-        self.b4 = DiscriminatorEpilogue(channels[4], cmap_dim=cmap_dim, resolution=4, **epilogue_kwargs, **common)
+        self.b4 = DiscriminatorEpilogue(width[4], cmap_dim=cmap_dim, resolution=4, **epilogue_kwargs, **shared)
 
     def forward(self, img, c, update_emas=False, **block_kwargs):
         x = None
@@ -618,4 +579,4 @@ class Discriminator(torch.nn.Module):
         return self.b4(x, img, cmap)
 
     def extra_repr(self):
-        return f'c_dim={self.c_dim:d}, img_resolution={self.img_resolution:d}, img_channels={self.img_channels:d}'
+        return _describe(self, 'c_dim', 'img_resolution', 'img_channels')
