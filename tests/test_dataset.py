@@ -76,6 +76,16 @@ def test_packed_shard_round_trip(tmp_path, gold, name, pack):
     src.close()
 
 
+def test_device_batcher_has_no_cpu_path(tmp_path):
+    src = _open('train_2mod_labels')
+    sh = ds_mod.PackedShard(ds_mod.write_packed(src, str(tmp_path / 's.gtshard')), use_labels=True)
+    with pytest.raises(RuntimeError):
+        ds_mod.DeviceBatcher(sh, 'cpu')
+    with pytest.raises(AssertionError):
+        ds_mod.PackedShard(ZIP)                               # not a packed shard
+    src.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', list(VARIANTS))
 @pytest.mark.parametrize('pack', ['float32', 'float16', 'uint16'])
