@@ -12,6 +12,7 @@ higher-order graph is being recorded, and the same formulas written with tensor 
 `applicable(x)` says whether a tensor can take the fused route (CUDA, fp16/fp32, dense channels-last, channel count the
 kernels support); callers keep the reference's op-by-op sequence otherwise.
 """
+import numpy as np
 import torch
 
 from ... import _lib
@@ -246,9 +247,22 @@ def demod_act(x, d=None, noise=None, b=None, act='linear', alpha=0.2, gain=1.0, 
 # parameter / style side: pre-normalisation + demodulation coefficients (csrc/modprep.cu)
 # ---------------------------------------------------------------------------------------------------------------------
 
+def prep_tensor_ops(weight, styles, prenorm):
+    """The same three results as `prep` as plain tensor ops (S3/training/networks_stylegan2.py:52-63 without the [N,O,I,kh,kw]
+    product): differentiable to any order by autograd.  Used as the second-order form of `_ModPrep.backward`."""
+    if prenorm:
+        fan_in = weight.shape[1] * weight.shape[2] * weight.shape[3]
+        weight = weight * (1 / np.sqrt(fan_in) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+        styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
+    d = (styles.square() @ weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+    return (weight.to(torch.float16), styles, d) if prenorm else (None, None, d)
+
+
 def prep_applicable(weight, styles):
-    """First-order passes only: the path-length pass differentiates this backward and keeps the tensor-op form
-    (`rgb.op_by_op_torgb` is the switch the loss flips for that pass)."""
+    """The fused kernels implement the first derivative; under `create_graph` `_ModPrep.backward` switches to the tensor-op form
+    (`prep_tensor_ops`), so the op is closed under differentiation wherever it is used.  The path-length pass, which always
+    differentiates this backward, skips the detour and uses the tensor-op form directly (`rgb.op_by_op_torgb`, a speed switch,
+    not a correctness one)."""
     from . import rgb
     return (rgb.torgb_fused and weight.is_cuda and weight.dtype == torch.float32 and styles.dtype == torch.float32 and styles.ndim == 2
             and weight.ndim == 4 and 1 <= styles.shape[0] <= 64 and weight.shape[1] % 4 == 0 and styles.shape[1] == weight.shape[1])
@@ -282,17 +296,29 @@ class _ModPrep(torch.autograd.Function):
             d = torch.empty_like(q)
             _lib.check(lib.gt_modprep_rsqrt(_lib.ptr(q), _lib.ptr(d), N * O, 1e-8, st), 'gt_modprep_rsqrt')
         _lib.count_launch(3)
-        ctx.save_for_backward(W, sn, sn2, wsq, d, scale, amax, smax, sarg)
+        ctx.save_for_backward(W, sn, sn2, wsq, d, scale, amax, smax, sarg, weight, styles)
         ctx.prenorm = bool(prenorm)
         ctx.wshape = weight.shape
         return (w16, sn, d) if prenorm else (None, None, d)
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g_w, g_sn, g_d):
         from . import fc
         lib = _lib.load()
-        W, sn, sn2, wsq, d, scale, amax, smax, sarg = ctx.saved_tensors
+        W, sn, sn2, wsq, d, scale, amax, smax, sarg, weight_in, styles_in = ctx.saved_tensors
+        if torch.is_grad_enabled():          # only true inside backward(create_graph=True)
+            # create_graph: someone will differentiate this backward -> evaluate it as the vector-Jacobian product of the
+            # tensor-op form, which autograd can differentiate again (w.r.t. the incoming gradients, the weight and the styles)
+            with torch.enable_grad():
+                wi = weight_in if weight_in.requires_grad else weight_in.detach().requires_grad_(True)
+                si = styles_in if styles_in.requires_grad else styles_in.detach().requires_grad_(True)
+                outs = prep_tensor_ops(wi, si, ctx.prenorm)
+                pairs = [(o, g) for o, g in zip(outs, (g_w, g_sn, g_d)) if o is not None and g is not None]
+                want = [t for t, need in ((wi, ctx.needs_input_grad[0]), (si, ctx.needs_input_grad[1])) if need]
+                got = list(torch.autograd.grad([o for o, _ in pairs], want, [g.to(o.dtype) for o, g in pairs], create_graph=True, allow_unused=True))
+            gW2 = got.pop(0) if ctx.needs_input_grad[0] else None
+            gs2 = got.pop(0) if ctx.needs_input_grad[1] else None
+            return gW2, gs2, None
         O, I, kh, kw = ctx.wshape
         N = sn.shape[0]
         if g_d is None:

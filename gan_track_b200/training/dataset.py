@@ -324,14 +324,23 @@ class DeviceBatcher:
         self.xflip = torch.from_numpy(shard._xflip.copy()).to(self.device)
         self.labels = torch.from_numpy(np.stack([shard.get_label(i) for i in range(len(shard))])).to(self.device) if len(shard) else None
         self.sampler = None
+        self.check_device_indices = True
 
     def batch(self, indices, scale=127.5, shift=-1.0):
+        """-> (real_img float32 in [-1, 1] = raw / scale + shift, real_c).  NOTE the images are already normalised: pass them to
+        `Trainer.train_step(..., normalized=True)`.  `scale=1, shift=0` returns the raw [0, 255] values of the loader contract."""
         lib = _lib.load()
         if not isinstance(indices, torch.Tensor) or not indices.is_cuda:
             host = np.asarray(indices.cpu() if isinstance(indices, torch.Tensor) else indices, dtype=np.int64)
             if host.size == 0 or host.min() < 0 or host.max() >= len(self.shard):
                 raise RuntimeError(f'gan_track_b200: dataset index out of range [0, {len(self.shard)})')
             indices = torch.from_numpy(host)
+        elif self.check_device_indices:
+            # device-resident indices: one min / max reduction and a host read (switch off for a sync-free loop whose indices
+            # are known good); without it a bad id would surface as NaN pixels plus a device-side assert in index_select
+            lo, hi = (int(v) for v in torch.stack([indices.min(), indices.max()]).tolist()) if indices.numel() else (0, -1)
+            if indices.numel() == 0 or lo < 0 or hi >= len(self.shard):
+                raise RuntimeError(f'gan_track_b200: dataset index out of range [0, {len(self.shard)})')
         idx = indices.to(device=self.device, dtype=torch.int64, non_blocking=True)
         b = idx.numel()
         n, c, h, w = self.images.shape

@@ -200,6 +200,10 @@ class Trainer:
         grid_sample_gradfix.enabled = True
 
         self.use_graphs = bool(use_graphs) and self.device.type == 'cuda'
+        if self.use_graphs and cfg.loss_kwargs.get('blur_fade_kimg', 0) != 0:
+            # a captured phase freezes host-side scalars derived from cur_nimg (blur_sigma and the blur taps, loss.py) at their
+            # capture-time value, whereas the reference fades them (S3/training/loss.py:70); the StyleGAN2 configs use 0
+            raise ValueError('use_graphs=True needs blur_fade_kimg == 0 (the blur schedule is a host-side function of cur_nimg)')
         dev = self.device
         self.G = networks.Generator(**cfg.G_kwargs, **cfg.common).train().requires_grad_(False).to(dev)
         self.D = networks.Discriminator(**cfg.D_kwargs, **cfg.common).train().requires_grad_(False).to(dev)
@@ -267,13 +271,19 @@ class Trainer:
             t = t.pin_memory()
         return t.to(self.device, non_blocking=True)
 
-    def train_step(self, real_img, real_c):
+    def train_step(self, real_img, real_c, normalized=False):
         """One iteration over this rank's share of the global batch.
-        real_img: [batch_size / num_gpus, C, H, W] float32 in [0, 255] (host or device; the loader's contract,
-        S3/training/dataset_mi_multimodal.py:259-264); real_c: one-hot labels [.., c_dim]."""
+        real_img: [batch_size / num_gpus, C, H, W]; real_c: one-hot labels [.., c_dim].
+        normalized=False (the reference loop's contract): float32 in [0, 255] as the loader delivers it
+        (S3/training/dataset_mi_multimodal.py:259-264), mapped to [-1, 1] here like training_loop_mi_multimodal.py:317.
+        normalized=True: already in [-1, 1] -- what `dataset.DeviceBatcher.batch()` / `.iterate()` return (the gather kernel
+        applies the `/127.5 - 1` itself), so feed those with `normalized=True` or the reals would be normalised twice."""
         cfg, dev = self.cfg, self.device
         batch_gpu = cfg.batch_gpu
-        real_img = (real_img.to(dev, non_blocking=True).to(torch.float32) / 127.5 - 1).split(batch_gpu)
+        real_img = real_img.to(dev, non_blocking=True).to(torch.float32)
+        if not normalized:
+            real_img = real_img / 127.5 - 1
+        real_img = real_img.split(batch_gpu)
         real_c = real_c.to(dev, non_blocking=True).split(batch_gpu)
         # Like the reference (:319-323) every rank draws len(phases) * GLOBAL batch latents and uses the leading
         # batch_size / num_gpus of each phase's chunk (zip() below stops at the number of real micro-batches).
@@ -286,7 +296,10 @@ class Trainer:
             if self.batch_idx % phase.interval != 0:
                 continue
             self.phase_counts[phase.name] += 1
-            if self.use_graphs and len(real_img) == 1:
+            if self.use_graphs:
+                # one optimiser state per module: the graphed path steps `flat_opt`, the eager path torch's Adam -- never mix them
+                if len(real_img) != 1:
+                    raise RuntimeError(f'graph mode runs one micro-batch per phase: got {sum(len(r) for r in real_img)} images for batch_gpu={batch_gpu}')
                 self._run_phase_graphed(phase, real_img[0], real_c[0], phase_gen_z[0], phase_gen_c[0])
             else:
                 self._run_phase_eager(phase, real_img, real_c, phase_gen_z, phase_gen_c)

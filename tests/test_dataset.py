@@ -120,3 +120,47 @@ def test_device_batcher_matches_reference_batches(tmp_path, gold, name, pack):
     with pytest.raises(RuntimeError):
         ds_mod.DeviceBatcher(sh, 'cpu')
     src.close()
+
+
+@pytest.mark.gpu
+def test_trainer_fed_from_device_batcher_sees_reference_reals(tmp_path, gold):
+    """Loader and loop connected: `DeviceBatcher.iterate()` already delivers `/127.5 - 1`-normalised slices, so they go into
+    `Trainer.train_step(..., normalized=True)`; the images the loss receives must be exactly the reference loop's
+    `real_img` (training_loop_mi_multimodal.py:313-318), not normalised a second time.  Device-side index tensors are range
+    checked too (RuntimeError, not a device-side assert)."""
+    from gan_track_b200.training import training_loop as tl
+    name = 'train_1mod_flip_max6'
+    kw = VARIANTS[name]
+    src = _open(name)
+    sh = ds_mod.PackedShard(ds_mod.write_packed(src, str(tmp_path / 'feed.gtshard')), max_size=kw['max_size'], use_labels=kw['use_labels'],
+                            xflip=kw['xflip'], random_seed=kw['random_seed'])
+    bat = ds_mod.DeviceBatcher(sh, 'cuda')
+    c, h, w = sh.image_shape
+    assert c == 1 and h == w
+    cfg = tl.claro_config(resolution=h, batch=4, num_gpus=1, cbase=1024, cmax=64, map_depth=2, cond=bool(kw['use_labels']))
+    trainer = tl.Trainer(cfg, rank=0, device='cuda')
+    seen = []
+    orig = trainer.loss.accumulate_gradients
+
+    def spy(**k):
+        seen.append(k['real_img'].detach().clone())
+        return orig(**k)
+    trainer.loss.accumulate_gradients = spy
+    it = bat.iterate(batch_size=4, rank=0, num_replicas=1, seed=5)
+    img, lab = next(it)
+    if lab.shape[1] != cfg.common.c_dim:
+        lab = torch.zeros([4, cfg.common.c_dim], device='cuda')
+    trainer.train_step(img, lab, normalized=True)
+    want = torch.from_numpy(gold[f'{name}/normalised'][gold[f'{name}/sampler/single'][:4]]).cuda()
+    assert len(seen) >= 2 and all(torch.equal(s, want) for s in seen)
+    assert float(want.min()) >= -1.0 and float(want.max()) <= 1.0 and float(want.max() - want.min()) > 0.5
+    # the raw contract gives the same reals through the default path
+    seen.clear()
+    raw, _ = bat.batch(gold[f'{name}/sampler/single'][:4], scale=1.0, shift=0.0)
+    trainer.train_step(raw, lab)
+    assert all(torch.allclose(s, want, atol=1e-6) for s in seen)
+    with pytest.raises(RuntimeError):
+        bat.batch(torch.tensor([0, len(sh)], device='cuda'))
+    with pytest.raises(RuntimeError):
+        bat.batch(torch.tensor([-1], device='cuda'))
+    src.close()
