@@ -35,7 +35,11 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--res', type=int, default=256)
-    ap.add_argument('--batch-gpu', type=int, default=32)
+    ap.add_argument('--batch-gpu', type=int, default=32, help='images per GPU per step (weak scaling: the default, global batch = 32 x N)')
+    ap.add_argument('--global-batch', type=int, default=None, help='fixed GLOBAL batch split over the N ranks (strong scaling, BASELINE configs 3 / 4: '
+                    'batch 64 over 2/4/8 GPUs, batch_gpu = B // N as S3/train_mi_multimodal.py:260); overrides --batch-gpu')
+    ap.add_argument('--no-igemm', action='store_true', help='A/B switch: route every convolution to the library (conv_backend.allow_igemm = False)')
+    ap.add_argument('--no-library', action='store_true', help='fail instead of routing any convolution to the library (conv_backend.allow_library = False)')
     ap.add_argument('--cbase', type=int, default=None)
     ap.add_argument('--aug', default='ada', choices=['ada', 'noaug'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -145,7 +149,9 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': 'train kimg/s, StyleGAN2-ADA %dx%d 1-ch' % (res, res), 'value': kimg_s, 'unit': 'kimg/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1000.0, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'claro_stylegan2-ada shape {res}x{res} 1-ch cbase {cbase} map-depth 8, ADA={args.aug}, CPU ref path', 'global_batch': args.cpu_batch},
+        'config': {'workload': f'claro_stylegan2-ada shape {res}x{res} 1-ch cbase {cbase} map-depth 8, ADA={args.aug}; CPU port: the oracle restatement of the '
+                               f"reference's ref-impl ops (oracle/ops_ref.py) under this repository's host code (the Python reference cannot travel to the GPU box)",
+                   'global_batch': args.cpu_batch},
         'cpu_baseline': {'value': kimg_s, 'unit': 'kimg/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': kimg_s, 'unit': 'kimg/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -181,9 +187,29 @@ def cpu_baseline_sample(res, cbase, aug, batch=4):
 
 # ------------------------------------------------------------------------------------------------ our arm
 
-# The kernel with the largest share of the step's GPU time in the committed step profile (profiles/r01_step_profile.txt);
-# `roofline` reports this one, `roofline_all` every hot kernel measured the same way.
-DOMINANT = 'conv_igemm_halo fwd 3x3 64->64 @256x256'
+# `roofline` reports the hot kernel with the largest share of the step, DERIVED from the run: every convolution call of one replay of
+# each captured phase is logged by shape (conv_igemm.call_log), multiplied by the phase's replays in the timed region and by the
+# per-launch time measured live in `hot_kernel_rooflines`; the case below is only the fallback when graphs are off.
+DOMINANT_FALLBACK = 'conv_igemm_halo fwd 3x3 64->64 @256x256'
+
+
+def dominant_kernel(trainer, phase_counts, roof_all, batch_gpu):
+    """-> (case name, {case: ms per step}) over the convolution cases of `roof_all` (measured at batch 32: scaled by batch)."""
+    per_step = {}
+    steps = max(1, max(phase_counts.values()) if phase_counts else 1)
+    for ph in trainer.phases:
+        shapes = ph.get('conv_shapes')
+        if not shapes:
+            continue
+        for (kind, n, cin, cout, h, w, k, stride, transpose), calls in shapes.items():
+            if k != 3 or stride != 1 or transpose:
+                continue
+            name = (f'conv_igemm_halo fwd 3x3 {cin}->{cout} @{h}x{w}' if kind == 'fwd' else f'conv_wgrad_halo 3x3 {cin}x{cout} over 32x{h}x{w} pixels')
+            if name in roof_all:
+                per_step[name] = per_step.get(name, 0.0) + calls * phase_counts.get(ph.name, 0) / steps * roof_all[name]['ms_per_launch'] * n / 32.0
+    if not per_step:
+        return DOMINANT_FALLBACK, {}
+    return max(per_step, key=per_step.get), {k: round(v, 3) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}
 
 
 def hot_kernel_rooflines(device, pk):
@@ -334,7 +360,15 @@ def run_ours(args):
     res = args.res
     cbase = args.cbase or (16384 if res <= 256 else 32768)
     batch_gpu = args.batch_gpu
+    scaling = 'weak'
+    if args.global_batch is not None:
+        assert args.global_batch % world == 0, '--global-batch must divide over the ranks'
+        batch_gpu, scaling = args.global_batch // world, 'strong'
     global_batch = batch_gpu * world
+    conv_backend.allow_igemm = not args.no_igemm
+    conv_backend.allow_library = not args.no_library
+    from gan_track_b200.torch_utils.ops import conv_igemm
+    conv_igemm.call_log = {}
     gamma = 0.0002 * res ** 2 / global_batch if res != 256 or global_batch != 32 else 0.4096
     cfg = tl.claro_config(resolution=res, batch=global_batch, num_gpus=world, cbase=cbase, aug=args.aug, gamma=gamma)
     trainer = tl.Trainer(cfg, rank=rank, device=device, overlap=not args.no_overlap, use_graphs=not args.no_graphs, merge_d_passes=not args.two_pass_dmain)
@@ -359,6 +393,9 @@ def run_ours(args):
     # Graph mode captures each phase at its second occurrence; Dreg runs every 16th iteration, so 17 warm-up iterations put
     # every capture before the timed region.
     n_warm = max(args.warmup, 3) if args.no_graphs else max(args.warmup, 17)
+    if n_warm != args.warmup and rank == 0:
+        print(f'bench.py: --warmup {args.warmup} raised to {n_warm}: every phase graph (Dreg runs every 16th iteration) is captured at its second '
+              f'occurrence and must be captured before the timed region; the JSON line reports warmup={n_warm}', file=sys.stderr, flush=True)
     for _ in range(n_warm):
         trainer.train_step(dev_img, dev_c)
 
@@ -414,7 +451,10 @@ def run_ours(args):
 
     pk = peaks()
     roof_all = hot_kernel_rooflines(device, pk) if rank == 0 else None
-    roof = dict(roof_all[DOMINANT], case=DOMINANT) if roof_all else None
+    roof = None
+    if roof_all:
+        dom, dom_ms = dominant_kernel(trainer, phase_counts, roof_all, batch_gpu)
+        roof = dict(roof_all[dom], case=dom, derived_from='conv call log x phase replays x live per-launch time (ms per step by case)', ms_per_step_by_case=dom_ms)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -426,13 +466,13 @@ def run_ours(args):
         flops_per_img = {256: 399e9, 512: 1597e9}.get(res)
         line = {
             'metric': 'train kimg/s, StyleGAN2-ADA %dx%d 1-ch' % (res, res), 'value': value, 'unit': 'kimg/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': n_warm, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'warmup': n_warm, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
             'dtype': 'f16', 'data': 'synthetic',
             'config': {'workload': f'claro_stylegan2-ada shape: {res}x{res} 1-ch, batch {batch_gpu}/GPU, cbase {cbase}, map-depth 8, fp16 top-4 resolutions, '
                                    f'lazy R1 (every 16) + path-length (every 4), ADA={args.aug}', 'global_batch': global_batch, 'batch_gpu': batch_gpu,
                        'parallelism': f'dp{world}', 'phase_counts_in_timed_region': phase_counts,
                        'l2_policy': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush in the step loop',
-                       'conv_routes': conv_stats, 'cuda_graphs': not args.no_graphs, 'dmain_one_pass': not args.two_pass_dmain, 'phase_ms': phase_ms},
+                       'conv_routes': conv_stats, 'allow_igemm': conv_backend.allow_igemm, 'allow_library': conv_backend.allow_library, 'cuda_graphs': not args.no_graphs, 'dmain_one_pass': not args.two_pass_dmain, 'phase_ms': phase_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base, 'roofline_all': roof_all,
         }
         if flops_per_img:

@@ -20,6 +20,9 @@ _igemm_forward = None
 _igemm_wgrad = None
 
 allow_igemm = True
+# False: a convolution outside the coverage of this package's kernels raises instead of going to the library (bench.py --no-library and
+# the GPU test that pins the 256x256 model to the repository's own kernels); the default keeps the reference's own route (F.conv2d) as fallback
+allow_library = True
 
 # fp32 layers must be true fp32 (north star: 1e-5 relative; the reference turns TF32 off in its training loop,
 # S3/training/training_loop_mi_multimodal.py:169-170).  The library route would otherwise silently use TF32.
@@ -38,6 +41,9 @@ def conv_forward(x, w, *, transpose, output_padding, stride, padding, groups):
         if y is not None:
             stats['igemm'] += 1
             return y
+    if not allow_library:
+        raise RuntimeError(f'conv_backend: no kernel of this package covers conv x{tuple(x.shape)} {x.dtype} w{tuple(w.shape)} stride {tuple(stride)} '
+                           f'padding {tuple(padding)} transpose {transpose} groups {groups} and allow_library is False')
     stats['library'] += 1
     return _aten_conv(x, w, stride, padding, transpose, output_padding, groups)
 
@@ -49,6 +55,9 @@ def conv_wgrad(dy, x, weight_shape, *, transpose, output_padding, stride, paddin
         if dw is not None:
             stats['igemm_wgrad'] += 1
             return dw
+    if not allow_library:
+        raise RuntimeError(f'conv_backend: no weight-gradient kernel of this package covers dy{tuple(dy.shape)} x{tuple(x.shape)} {x.dtype} w{tuple(weight_shape)} '
+                           f'stride {tuple(stride)} transpose {transpose} groups {groups} and allow_library is False')
     stats['library_wgrad'] += 1
     w_dummy = torch.empty(weight_shape, dtype=x.dtype, device=x.device)
     _, dw, _ = torch.ops.aten.convolution_backward(dy, x, w_dummy, None, list(stride), list(padding), [1, 1], transpose,

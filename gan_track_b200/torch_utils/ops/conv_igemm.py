@@ -11,6 +11,16 @@ from ... import _lib
 
 enabled = True
 
+# {(kind, N, Cin, Cout, H, W, k, stride, transpose): calls} when a dict is installed (bench.py: which convolution shape carries the
+# step); Trainer snapshots it around a graph capture so that replays are accounted for.
+call_log = None
+
+
+def _log(kind, N, cin, cout, H, W, k, stride, transpose):
+    if call_log is not None:
+        key = (kind, int(N), int(cin), int(cout), int(H), int(W), int(k), int(stride), bool(transpose))
+        call_log[key] = call_log.get(key, 0) + 1
+
 
 def _nhwc(t):
     """t as an NHWC-strided tensor whose strides the TMA unit accepts."""
@@ -128,6 +138,7 @@ def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, p
     OH, OW = out_size(H, W, kh, kw, stride[0], padding[0], transpose)
     if OH <= 0 or OW <= 0:
         return None
+    _log('fwd', N, cin, cout, H, W, kh, stride[0], transpose)
     with torch.cuda.device(x.device):
         if packed is None:
             packed = pack_weight(w, transpose)
@@ -161,6 +172,7 @@ def igemm_wgrad(dy, x, weight_shape, *, transpose, output_padding, stride, paddi
     u, s = _nhwc(u), _nhwc(s)
     N, UC, UH, UW = u.shape
     _, SC, SH, SW = s.shape
+    _log('wgrad', N, SC, UC, SH, SW, kh, stride[0], transpose)
     with torch.cuda.device(x.device):
         nws = lib.gt_conv2d_wgrad_workspace(N, UH, UW, UC, SC, kh, kw)
         ws = torch.empty([nws], dtype=torch.float32, device=x.device)

@@ -387,6 +387,8 @@ class Trainer:
             return
         if phase.graphs is None:                                  # capture (does not execute), then replay below
             launches0, conv0 = _lib.launches, dict(conv_backend.stats)
+            from ..torch_utils.ops import conv_igemm
+            log0 = dict(conv_igemm.call_log) if conv_igemm.call_log is not None else None
             torch.cuda.synchronize()
             ga = torch.cuda.CUDAGraph()
             if self.num_gpus == 1:
@@ -403,6 +405,10 @@ class Trainer:
                 phase.graphs = (ga, gb)
             # the Python-side launch / route counters only tick at capture time; remember the per-replay amounts
             phase.replay_counts = (_lib.launches - launches0, {k: conv_backend.stats[k] - conv0[k] for k in conv0})
+            if log0 is not None:        # convolution shapes of one replay of this phase (bench.py derives the dominant kernel from it)
+                phase.conv_shapes = {k: v - log0.get(k, 0) for k, v in conv_igemm.call_log.items() if v != log0.get(k, 0)}
+                conv_igemm.call_log.clear()
+                conv_igemm.call_log.update(log0)
             _lib.launches = launches0
             conv_backend.stats.update(conv0)
         ga, gb = phase.graphs
