@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     const int nkb = ph.ntaps * kchunks;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < ph.ntaps; t++) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(BM, BN, 0, 0, 0), idesc_tf32 = umma_idesc(BM, BN, 2, 0, 0);
             constexpr bool tf32 = MODE == CONV_TF32;
             int stage = 0;

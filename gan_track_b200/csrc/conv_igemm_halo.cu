@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
     const uint32_t row_pitch = (uint32_t)p.halo_w * 128u;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t a_it = 0, b_it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const Item it = decode_item(p, item, TILE_W);
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0, 0), idesc_tf32 = umma_idesc(128, BN, 2, 0, 0);
             constexpr bool tf32 = MODE == CONV_TF32;
             uint32_t a_it = 0, b_it = 0, t_it = 0;

@@ -153,7 +153,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     const uint32_t row_pitch = (uint32_t)p.halo_w * 128u;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t a_it = 0, b_it = 0;
             for (int item = cluster_id; item < total_items; item += num_clusters) {
                 const Item2 it = decode_item2(p, item, PAIR_W);
@@ -178,7 +178,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = umma_idesc(256, BN, 0, 0, 0);
             uint32_t a_it = 0, b_it = 0, t_it = 0;
             for (int item = cluster_id; item < total_items; item += num_clusters) {

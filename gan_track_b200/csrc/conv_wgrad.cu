@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
     const int bw_log2 = p.bw_log2, bh_log2 = p.bh_log2, bn_log2 = 6 - bw_log2 - bh_log2;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t bytes = L::U_BYTES + (uint32_t)ntap * L::S_TAP_BYTES;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(WM, BN, 0, 1, 1);   // both operands MN-major
             int stage = 0;
             uint32_t phase = 0;

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = split; t < p.num_tiles; t += p.splits) {
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __gr
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(128, 64, 0, 1, 1);   // both operands MN-major
             constexpr uint32_t pitch = HW_ * 128;                      // bytes between tile rows of the staged S footprint
             int stage = 0;

@@ -51,8 +51,10 @@ struct ProbeArgs {
     int halo;           // 0: dense A tile per sub-tile (SBO 1024, 16 KB apart); 1: halo view (SBO = pitch, sub-tile j at +j*1024)
     int shift;          // 1: tap t starts (t/3) rows and (t%3) pixels into the halo (unaligned start); 0: every tap at offset 0
     int pitch;          // halo row pitch in bytes
-    int b_rotate;       // 1: tap t reads weight slab t (9 resident slabs); 0: always slab 0
+    int b_rotate;       // 1: tap t reads weight slab t (nslabs resident slabs); 0: always slab 0
     int bn;
+    int a_kb;           // KB of the A region
+    int nslabs;         // weight slabs resident in shared memory
 };
 
 // dynamic smem: [A: 96 KB][B: 9 * BN * 128]  (zero filled)
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, long long* o
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_bytes = 96 * 1024, b_bytes = 9u * (uint32_t)(a.bn / CG) * 128u;
+    const uint32_t a_bytes = (uint32_t)a.a_kb * 1024u, b_bytes = (uint32_t)a.nslabs * (uint32_t)(a.bn / CG) * 128u;
     for (uint32_t i = threadIdx.x * 16; i < a_bytes + b_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     if (threadIdx.x == 0) {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, long long* o
         for (int it = 0; it < a.iters; it++) {
             for (int t = 0; t < 9; t++) {
                 const uint32_t at = a0 + (a.shift ? (uint32_t)(t / 3) * (uint32_t)a.pitch + (uint32_t)(t % 3) * 128u : 0u);
-                const uint32_t bt = b0 + (a.b_rotate ? (uint32_t)t * slab : 0u);
+                const uint32_t bt = b0 + (a.b_rotate ? (uint32_t)(t % a.nslabs) * slab : 0u);
                 for (int j = 0; j < a.mt; j++) {
                     const uint32_t aj = at + (a.halo ? (uint32_t)j * 1024u : (uint32_t)j * 16384u);
 #pragma unroll
@@ -121,8 +123,11 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs a, long long* o
 
 template <int CG>
 static double run(const ProbeArgs& a, long long* d_out, int sms) {
-    const size_t smem = 96 * 1024 + 9 * (size_t)(a.bn / CG) * 128 + 1024;
-    cudaFuncSetAttribute(probe_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)a.a_kb * 1024 + (size_t)a.nslabs * (size_t)(a.bn / CG) * 128 + 1024;
+    if (cudaFuncSetAttribute(probe_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        printf("cannot reserve %zu bytes of shared memory\n", smem);
+        exit(1);
+    }
     cudaMemset(d_out, 0, sizeof(long long) * sms);
     if (CG == 1) {
         probe_kernel<1><<<sms, 128, smem>>>(a, d_out);
@@ -140,7 +145,8 @@ static double run(const ProbeArgs& a, long long* d_out, int sms) {
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, probe_kernel<2>, a, d_out);
     }
-    cudaError_t e = cudaDeviceSynchronize();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("CUDA error: %s\n", cudaGetErrorString(e));
         exit(1);
@@ -187,6 +193,9 @@ int main() {
                 a.pitch = (8 * mt + 2) * 128;
                 a.b_rotate = l.b_rotate;
                 a.bn = bn;
+                a.a_kb = bn == 64 ? 80 : 48;
+                a.nslabs = bn == 64 ? 9 : (bn == 128 ? 9 : 4);
+                if (cg == 1 && bn == 128) a.nslabs = 9;      // 48 + 144 KB
                 if (!l.halo && l.shift) a.pitch = 0;               // dense tile: shift by whole pixels (128-byte rows) only
                 run<1>(a, d_out, sms);      // warm-up
                 const double c = cg == 1 ? run<1>(a, d_out, sms) : run<2>(a, d_out, sms);
@@ -206,8 +215,28 @@ int main() {
         a.pitch = 10 * 128;
         a.b_rotate = 1;
         a.bn = bn;
+        a.a_kb = 48;
+        a.nslabs = 9;
         const double c = run<1>(a, d_out, sms);
         printf("  cg::1  %-4d %-3d %-28s %10.1f %10.1f %8.2f\n", bn, 1, "halo pitch 10 px, shifted", c, 128.0 * bn / 256.0, c / (128.0 * bn / 256.0));
+    }
+    // row-streaming form of a 64->64 3x3 convolution: A = one input row strip of 128 pixels (dense, start shifted by dx pixels),
+    // B = the three dy taps of one dx stacked along N (192 rows) -> every MMA feeds three output rows
+    printf("# row-streaming patterns (A dense 128-pixel strip, shifted start; B = N rows of resident weights)\n");
+    for (int bn : {64, 128, 192, 256}) {
+        ProbeArgs a;
+        a.iters = 128;
+        a.mt = 1;
+        a.halo = 0;
+        a.shift = 1;
+        a.pitch = 0;
+        a.b_rotate = 1;
+        a.bn = bn;
+        a.a_kb = 48;
+        a.nslabs = bn <= 128 ? 9 : (bn == 192 ? 6 : 4);
+        run<1>(a, d_out, sms);
+        const double c = run<1>(a, d_out, sms);
+        printf("  cg::1  %-4d %-3d %-28s %10.1f %10.1f %8.2f\n", bn, 1, "strip A shifted, N rows of B", c, 128.0 * bn / 256.0, c / (128.0 * bn / 256.0));
     }
     cudaFree(d_out);
     return 0;
