@@ -59,9 +59,13 @@ _PROTOTYPES = {
     'gt_conv_wgrad_config': (_i, [_i]),
     'gt_conv_pack_weight_f16': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
     'gt_conv2d_igemm_f16': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    'gt_split_tf32x3': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
-    'gt_conv_pack_weight_tf32x3': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
-    'gt_conv2d_igemm_tf32': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'gt_f16x3_amax': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
+    'gt_f16x3_split_act': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'gt_f16x3_pack_weight': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'gt_conv2d_igemm_f16_f32out': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _vp]),
+    'gt_f16x3_slab_reduce': (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp, _vp, _vp]),
+    'gt_conv2d_wgrad_f16x3_workspace': (_ll, [_i, _i, _i, _i, _i, _i, _i]),
+    'gt_conv2d_wgrad_f16x3': (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp]),
     'gt_conv2d_igemm_f16_bias_act': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp]),
     'gt_conv2d_wgrad_workspace': (_ll, [_i, _i, _i, _i, _i, _i, _i]),
     'gt_conv2d_wgrad_f16': (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _ll, _vp, _ll, _vp]),

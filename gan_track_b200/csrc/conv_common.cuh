@@ -14,6 +14,7 @@ struct ConvPhase {
     int ntaps;
     int OHp, OWp;        // extent of this phase's output grid
     int off_y, off_x;    // output pixel = (a * out_stride + off_y, b * out_stride + off_x)
+    long long y_off;     // element offset of this phase's output slab (K-split phases of the fp32-output mode write partial sums side by side)
     int8_t tdy[CONV_MAX_TAPS], tdx[CONV_MAX_TAPS], tw[CONV_MAX_TAPS];   // input offset of the tap, weight slab of the tap
 };
 
@@ -25,9 +26,9 @@ struct ConvParams {
     int bw_log2, bh_log2;            // (per-tap kernel) tile box bw x bh x bn pixels, product 128
     int tiles_w, tiles_h, tiles_n;   // over the largest phase
     int n_tiles;                     // Cout / BN
-    void* y;                         // fp16 (tf32 == 0) or fp32 (tf32 == 1) NHWC output
+    void* y;                         // fp16 (f32out == 0) or fp32 (f32out == 1) NHWC output
     long long ys_n, ys_h, ys_w;      // element strides
-    int tf32;                        // 1: operands are fp32 bit patterns consumed as TF32 (32 channels per 128-byte chunk), fp32 output
+    int f32out;                      // 1: raw fp32 accumulators are stored (fp16x3 route of the fp32 layers, csrc/conv_f16x3.cu); operands stay fp16
     // optional fused epilogue (fp16 output only): y = clamp(act(round_fp16(acc) + bias[co]) * gain), the bias_act that follows the
     // convolution in Conv2dLayer.forward (S3/training/networks_stylegan2.py:176-177); ep_act 0 = plain store
     const __half* ep_bias;
@@ -40,14 +41,14 @@ struct ConvParams {
 };
 
 // Kernel flavours (compile-time, so that the plain fp16 path carries none of the others' code or registers):
-enum { CONV_F16 = 0, CONV_TF32 = 1, CONV_F16_EP = 2 };
-__host__ __device__ inline int conv_mode(const ConvParams& p) { return p.tf32 ? CONV_TF32 : (p.ep_act != 0 ? CONV_F16_EP : CONV_F16); }
+enum { CONV_F16 = 0, CONV_F32OUT = 1, CONV_F16_EP = 2 };
+__host__ __device__ inline int conv_mode(const ConvParams& p) { return p.f32out ? CONV_F32OUT : (p.ep_act != 0 ? CONV_F16_EP : CONV_F16); }
 
 // 32 consecutive accumulator columns (output channels co0 .. co0+31) of one output pixel -> global memory
 // (fp16: 64 bytes, fp32: 128 bytes); CONV_F16_EP runs the bias + activation epilogue on the way
 template <int MODE>
 __device__ __forceinline__ void conv_store32(const ConvParams& p, long long elem_off, int co0, const uint32_t (&r)[32]) {
-    if (MODE == CONV_TF32) {
+    if (MODE == CONV_F32OUT) {
         float* yp = (float*)p.y + elem_off;
 #pragma unroll
         for (int v = 0; v < 8; v++) *reinterpret_cast<uint4*>(yp + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);

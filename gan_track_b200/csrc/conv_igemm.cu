@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    constexpr int kel = MODE == CONV_TF32 ? 32 : BK;           // channels per 128-byte k-chunk
+    constexpr int kel = BK;                                    // channels per 128-byte k-chunk
     const int kchunks = p.Cin / kel;
     const int nkb = ph.ntaps * kchunks;
 
@@ -107,14 +107,14 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < ph.ntaps; t++) {
-                const int cy = oy0 * p.in_stride + ph.tdy[t], cx = ox0 * p.in_stride + ph.tdx[t];
-                const int slab = ph.tw[t];
-                for (int kc = 0; kc < kchunks; kc++) {
+            // channel chunks in the OUTER loop, taps inside (the order the fp16x3 route relies on: csrc/conv_f16x3.cu)
+            for (int kc = 0; kc < kchunks; kc++) {
+                for (int t = 0; t < ph.ntaps; t++) {
+                    const int cy = oy0 * p.in_stride + ph.tdy[t], cx = ox0 * p.in_stride + ph.tdx[t];
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
                     tma_load_4d(sA + stage * L::A_BYTES, &tmA, &full[stage], kc * kel, cx, cy, n0);
-                    tma_load_3d(sB + stage * L::B_BYTES, &tmB, &full[stage], kc * kel, nt * BN, slab);
+                    tma_load_3d(sB + stage * L::B_BYTES, &tmB, &full[stage], kc * kel, nt * BN, ph.tw[t]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -125,20 +125,17 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc(BM, BN, 0, 0, 0), idesc_tf32 = umma_idesc(BM, BN, 2, 0, 0);
-            constexpr bool tf32 = MODE == CONV_TF32;
+            constexpr uint32_t idesc = umma_idesc(BM, BN, 0, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA + stage * L::A_BYTES), b0 = smem_u32(sB + stage * L::B_BYTES);
-                // one MMA consumes 32 bytes of every row: K = 16 fp16 or K = 8 tf32 elements -- same byte geometry for both
+                // one MMA consumes 32 bytes of every row: K = 16 fp16 elements
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (tf32) umma_tf32(tmem_base, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc_tf32, (uint32_t)((kb | k) != 0));
-                    else umma_f16(tmem_base, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kb | k) != 0));
-                }
+                for (int k = 0; k < 4; k++)
+                    umma_f16(tmem_base, umma_smem_desc(a0 + k * 32, 0, 1024), umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kb | k) != 0));
                 umma_commit(&empty[stage]);   // stage reusable once these MMAs have read it
                 if (++stage == STAGES) {
                     stage = 0;
@@ -158,7 +155,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const __grid_const
         const int a = oy0 + lh, b = ox0 + lw, n = n0 + ln;
         const bool valid = (a < ph.OHp) && (b < ph.OWp) && (n < p.N);
         const long long yoff = (long long)n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
-                               (long long)(b * p.out_stride + ph.off_x) * p.ys_w + nt * BN;
+                               (long long)(b * p.out_stride + ph.off_x) * p.ys_w + nt * BN + ph.y_off;
         mbar_wait(tfull, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -218,7 +215,7 @@ int launch_conv_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPara
 template <int BN, int STAGES>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
     switch (conv_mode(p)) {
-        case CONV_TF32: return launch_conv_m<BN, STAGES, CONV_TF32>(tmA, tmB, p, stream);
+        case CONV_F32OUT: return launch_conv_m<BN, STAGES, CONV_F32OUT>(tmA, tmB, p, stream);
         case CONV_F16_EP: return launch_conv_m<BN, STAGES, CONV_F16_EP>(tmA, tmB, p, stream);
         default: return launch_conv_m<BN, STAGES, CONV_F16>(tmA, tmB, p, stream);
     }
@@ -255,10 +252,14 @@ extern "C" int gt_conv_pack_weight_f16(const void* w, long long s_co, long long 
 
 static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
                              long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
-                             int pad, int transposed, int tf32, const void* ep_bias, int ep_act, float ep_alpha, float ep_gain, float ep_clamp,
-                             void* stream) {
-    const int esz = tf32 ? 4 : 2, kel = tf32 ? 32 : BK, al = 16 / esz;
-    GT_REQUIRE(ep_act == 0 || (!tf32 && (ep_act == 1 || ep_act == 3)), "gt_conv2d_igemm: fused epilogue supports fp16 output with linear (1) or lrelu (3); got %d", ep_act);
+                             int pad, int transposed, int f32out, long long slab_stride, const void* ep_bias, int ep_act, float ep_alpha, float ep_gain,
+                             float ep_clamp, void* stream) {
+    // f32out: fp16 operands, raw fp32 accumulators stored; with slab_stride > 0 the reduction is additionally split by kernel row
+    // (one phase per row of taps, phase i writing its partial sum at y + i * slab_stride elements), which bounds the number of
+    // accumulator updates per stored value (see csrc/conv_f16x3.cu)
+    const int esz = 2, kel = BK, al = 8;
+    const int osz_al = f32out ? 4 : 8;
+    GT_REQUIRE(ep_act == 0 || (!f32out && (ep_act == 1 || ep_act == 3)), "gt_conv2d_igemm: fused epilogue supports fp16 output with linear (1) or lrelu (3); got %d", ep_act);
     GT_REQUIRE(ep_bias == nullptr || (((uintptr_t)ep_bias) & 15) == 0, "gt_conv2d_igemm: epilogue bias must be 16-byte aligned");
     GT_REQUIRE(x && wpacked && y, "gt_conv2d_igemm_f16: null pointer");
     GT_REQUIRE(N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "gt_conv2d_igemm_f16: empty tensor");
@@ -266,7 +267,7 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     GT_REQUIRE(KH * KW <= MAX_TAPS && KH >= 1 && KW >= 1, "gt_conv2d_igemm_f16: kernel %dx%d not supported", KH, KW);
     GT_REQUIRE(stride == 1 || stride == 2, "gt_conv2d_igemm_f16: stride %d not supported", stride);
     GT_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)y & 15) == 0, "gt_conv2d_igemm_f16: pointers must be 16-byte aligned");
-    GT_REQUIRE(xs_w % al == 0 && xs_h % al == 0 && xs_n % al == 0 && ys_w % al == 0 && ys_h % al == 0 && ys_n % al == 0,
+    GT_REQUIRE(xs_w % al == 0 && xs_h % al == 0 && xs_n % al == 0 && ys_w % osz_al == 0 && ys_h % osz_al == 0 && ys_n % osz_al == 0 && slab_stride % 4 == 0,
                "gt_conv2d_igemm: strides must be multiples of 16 bytes");
     GT_REQUIRE(pad >= 0 && pad < 8, "gt_conv2d_igemm_f16: pad %d not supported", pad);
 
@@ -276,7 +277,7 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     p.Cin = Cin;
     p.Cout = Cout;
     p.y = y;
-    p.tf32 = tf32;
+    p.f32out = f32out;
     p.ep_bias = (const __half*)ep_bias;
     p.ep_act = ep_act;
     p.ep_alpha = ep_alpha;
@@ -287,34 +288,44 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     p.ys_w = ys_w;
     if (!transposed) {
         GT_REQUIRE(OH == (H + 2 * pad - KH) / stride + 1 && OW == (W + 2 * pad - KW) / stride + 1, "gt_conv2d_igemm_f16: output size mismatch");
-        p.nphases = 1;
+        const bool ksplit = f32out && slab_stride > 0 && KH > 1;
+        GT_REQUIRE(!ksplit || KH <= CONV_MAX_PHASES, "gt_conv2d_igemm: K-split supports at most %d kernel rows", CONV_MAX_PHASES);
+        p.nphases = ksplit ? KH : 1;
         p.in_stride = stride;
         p.out_stride = 1;
-        ConvPhase& ph = p.ph[0];
-        ph.ntaps = KH * KW;
-        ph.OHp = OH;
-        ph.OWp = OW;
-        for (int r = 0; r < KH; r++)
+        for (int r = 0; r < KH; r++) {
+            ConvPhase& ph = p.ph[ksplit ? r : 0];
+            ph.OHp = OH;
+            ph.OWp = OW;
+            ph.y_off = ksplit ? (long long)r * slab_stride : 0;
             for (int s = 0; s < KW; s++) {
-                ph.tdy[r * KW + s] = (int8_t)(r - pad);
-                ph.tdx[r * KW + s] = (int8_t)(s - pad);
-                ph.tw[r * KW + s] = (int8_t)(r * KW + s);
+                const int t = ksplit ? s : r * KW + s;
+                ph.tdy[t] = (int8_t)(r - pad);
+                ph.tdx[t] = (int8_t)(s - pad);
+                ph.tw[t] = (int8_t)(r * KW + s);
+                ph.ntaps = t + 1;
             }
+        }
     } else if (stride == 1) {
         GT_REQUIRE(OH == H - 2 * pad + KH - 1 && OW == W - 2 * pad + KW - 1, "gt_conv2d_igemm_f16: output size mismatch (transposed)");
-        p.nphases = 1;
+        const bool ksplit = f32out && slab_stride > 0 && KH > 1;
+        GT_REQUIRE(!ksplit || KH <= CONV_MAX_PHASES, "gt_conv2d_igemm: K-split supports at most %d kernel rows", CONV_MAX_PHASES);
+        p.nphases = ksplit ? KH : 1;
         p.in_stride = 1;
         p.out_stride = 1;
-        ConvPhase& ph = p.ph[0];
-        ph.ntaps = KH * KW;
-        ph.OHp = OH;
-        ph.OWp = OW;
-        for (int r = 0; r < KH; r++)
+        for (int r = 0; r < KH; r++) {
+            ConvPhase& ph = p.ph[ksplit ? r : 0];
+            ph.OHp = OH;
+            ph.OWp = OW;
+            ph.y_off = ksplit ? (long long)r * slab_stride : 0;
             for (int s = 0; s < KW; s++) {
-                ph.tdy[r * KW + s] = (int8_t)(pad - r);
-                ph.tdx[r * KW + s] = (int8_t)(pad - s);
-                ph.tw[r * KW + s] = (int8_t)(r * KW + s);
+                const int t = ksplit ? s : r * KW + s;
+                ph.tdy[t] = (int8_t)(pad - r);
+                ph.tdx[t] = (int8_t)(pad - s);
+                ph.tw[t] = (int8_t)(r * KW + s);
+                ph.ntaps = t + 1;
             }
+        }
     } else {
         GT_REQUIRE(pad == 0, "gt_conv2d_igemm_f16: transposed stride-2 convolution supports pad 0 only");
         GT_REQUIRE(OH == (H - 1) * 2 + KH && OW == (W - 1) * 2 + KW, "gt_conv2d_igemm_f16: output size mismatch (transposed stride 2)");
@@ -366,7 +377,7 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
     p.n_tiles = Cout / BN;
 
-    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -396,8 +407,17 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
 extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
                                    long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
                                    int pad, int transposed, void* stream) {
-    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, nullptr, 0,
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, 0, nullptr, 0,
                              0.f, 1.f, -1.f, stream);
+}
+
+// fp16 operands, fp32 output (raw accumulators): the tensor-core half of the fp16x3 route for the fp32 layers (csrc/conv_f16x3.cu).
+// slab_stride > 0 and a kernel with several rows: one partial sum per kernel row at y + row * slab_stride (elements); the caller adds them.
+extern "C" int gt_conv2d_igemm_f16_f32out(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                                          long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
+                                          int pad, int transposed, long long slab_stride, void* stream) {
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 1, slab_stride,
+                             nullptr, 0, 0.f, 1.f, -1.f, stream);
 }
 
 // the same convolution with the layer's bias_act fused into the epilogue: y = clamp(act(conv + bias) * gain)
@@ -406,93 +426,6 @@ extern "C" int gt_conv2d_igemm_f16_bias_act(const void* x, long long xs_n, long 
                                             int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain, float clamp,
                                             void* stream) {
     GT_REQUIRE(act == 1 || act == 3, "gt_conv2d_igemm_f16_bias_act: act must be linear (1) or lrelu (3); got %d", act);
-    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, bias, act,
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, 0, bias, act,
                              alpha, gain, clamp, stream);
-}
-
-// ---- fp32 convolutions on the tensor cores: 3 x TF32 ------------------------------------------------------------------
-// The fp32 blocks (4x4 .. 16x16, 512 channels) must stay fp32-accurate (north star 1e-5; the reference turns TF32 off,
-// S3/training/training_loop_mi_multimodal.py:169-170).  A TF32 operand keeps 11 significant bits, so each fp32 value is
-// split into big = rna_tf32(v) and small = rna_tf32(v - big) (22 bits together) and the product is taken as
-//     x w  ~=  x_big w_big + x_big w_small + x_small w_big          (dropped: x_small w_small, ~2^-22 relative)
-// with fp32 accumulation in TMEM.  The three terms are ONE TF32 convolution over a 3x wider channel dimension:
-//     activations [N,H,W,3C] = [x_big | x_big | x_small],  weights [tap][Cout][3C] = [w_big | w_small | w_big]
-// which is what gt_split_tf32x3 / gt_conv_pack_weight_tf32x3 produce and gt_conv2d_igemm_tf32 (the same kernels as the fp16
-// path, kind::tf32, 32 channels per 128-byte chunk, fp32 output) consumes.
-__device__ __forceinline__ float rna_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-
-// x: [N,C,H,W] with arbitrary element strides  ->  out: [N,H,W,3C] contiguous
-__global__ void __launch_bounds__(256) split_tf32x3_kernel(const float* __restrict__ x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C,
-                                                           int H, int W, float* __restrict__ out) {
-    const long long total = (long long)N * H * W * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        long long r = i / C;
-        const int w = (int)(r % W);
-        r /= W;
-        const int h = (int)(r % H);
-        const int n = (int)(r / H);
-        const float v = x[n * s_n + c * s_c + h * s_h + w * s_w];
-        const float big = rna_tf32(v);
-        const float small = rna_tf32(v - big);
-        float* o = out + (i / C) * (3ll * C) + c;
-        o[0] = big;
-        o[C] = big;
-        o[2 * C] = small;
-    }
-}
-
-// out[t][co][0:C | C:2C | 2C:3C] = big | small | big of w[co * s_co + ci * s_ci + r * s_r + s * s_s]
-__global__ void __launch_bounds__(256) pack_weight_tf32x3_kernel(const float* __restrict__ w, long long s_co, long long s_ci, long long s_r, long long s_s,
-                                                                 int Cout, int Cin, int KH, int KW, float* __restrict__ out) {
-    const long long total = (long long)KH * KW * Cout * Cin;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ci = (int)(i % Cin);
-        long long r_ = i / Cin;
-        const int co = (int)(r_ % Cout);
-        const int t = (int)(r_ / Cout);
-        const int r = t / KW, s = t - r * KW;
-        const float v = w[co * s_co + ci * s_ci + r * s_r + s * s_s];
-        const float big = rna_tf32(v);
-        const float small = rna_tf32(v - big);
-        float* o = out + ((long long)t * Cout + co) * (3ll * Cin) + ci;
-        o[0] = big;
-        o[Cin] = small;
-        o[2 * Cin] = big;
-    }
-}
-
-extern "C" int gt_split_tf32x3(const void* x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C, int H, int W, void* out,
-                               void* stream) {
-    GT_REQUIRE(x && out, "gt_split_tf32x3: null pointer");
-    GT_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "gt_split_tf32x3: bad shape");
-    const long long total = (long long)N * H * W * C;
-    long long g = (total + 255) / 256;
-    if (g > (long long)gt_num_sms() * 16) g = (long long)gt_num_sms() * 16;
-    split_tf32x3_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)x, s_n, s_c, s_h, s_w, N, C, H, W, (float*)out);
-    GT_CUDA_LAUNCH_CHECK("gt_split_tf32x3");
-    return GT_OK;
-}
-
-extern "C" int gt_conv_pack_weight_tf32x3(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin, int KH, int KW,
-                                          void* out, void* stream) {
-    GT_REQUIRE(w && out, "gt_conv_pack_weight_tf32x3: null pointer");
-    GT_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "gt_conv_pack_weight_tf32x3: bad shape");
-    const long long total = (long long)KH * KW * Cout * Cin;
-    long long g = (total + 255) / 256;
-    if (g > (long long)gt_num_sms() * 16) g = (long long)gt_num_sms() * 16;
-    pack_weight_tf32x3_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)w, s_co, s_ci, s_r, s_s, Cout, Cin, KH, KW, (float*)out);
-    GT_CUDA_LAUNCH_CHECK("gt_conv_pack_weight_tf32x3");
-    return GT_OK;
-}
-
-extern "C" int gt_conv2d_igemm_tf32(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
-                                    long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
-                                    int pad, int transposed, void* stream) {
-    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 1, nullptr, 0,
-                             0.f, 1.f, -1.f, stream);
 }

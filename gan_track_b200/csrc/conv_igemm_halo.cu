@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    constexpr int kel = MODE == CONV_TF32 ? 32 : 64;           // channels per 128-byte chunk
+    constexpr int kel = 64;                                    // channels per 128-byte chunk
     const int kchunks = p.Cin / kel;
     const uint32_t a_bytes = (uint32_t)(p.halo_w * p.halo_h) * 128u;
     const uint32_t row_pitch = (uint32_t)p.halo_w * 128u;
@@ -135,8 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0, 0), idesc_tf32 = umma_idesc(128, BN, 2, 0, 0);
-            constexpr bool tf32 = MODE == CONV_TF32;
+            constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0, 0);
             uint32_t a_it = 0, b_it = 0, t_it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const Item it = decode_item(p, item, TILE_W);
@@ -161,14 +160,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
 #pragma unroll
                         for (int j = 0; j < MT; j++) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {      // 32 bytes of every row per MMA: K = 16 fp16 or K = 8 tf32
-                                if (tf32)
-                                    umma_tf32(acc + j * BN, umma_smem_desc(at + j * (SUB_W * 128) + k * 32, 0, row_pitch),
-                                              umma_smem_desc(b0 + k * 32, 0, 1024), idesc_tf32, (uint32_t)((kc | t | k) != 0));
-                                else
-                                    umma_f16(acc + j * BN, umma_smem_desc(at + j * (SUB_W * 128) + k * 32, 0, row_pitch),
-                                             umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kc | t | k) != 0));
-                            }
+                            for (int k = 0; k < 4; k++)        // 32 bytes of every row per MMA: K = 16 fp16
+                                umma_f16(acc + j * BN, umma_smem_desc(at + j * (SUB_W * 128) + k * 32, 0, row_pitch),
+                                         umma_smem_desc(b0 + k * 32, 0, 1024), idesc, (uint32_t)((kc | t | k) != 0));
                         }
                         umma_commit(&b_empty[bs]);
                         b_it++;
@@ -199,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
                 const int b = it.ox0 + j * SUB_W + lw;
                 const bool valid = (a < ph.OHp) && (b < ph.OWp) && !p.dbg_no_store;
                 const long long yoff = (long long)it.n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
-                                       (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN;
+                                       (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN + ph.y_off;
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; c++) {
                     uint32_t r[32];
@@ -244,7 +238,7 @@ int launch_halo_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPara
 template <int BN, int MT, int SB, int NBUF>
 int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
     switch (conv_mode(p)) {
-        case CONV_TF32: return launch_halo_m<BN, MT, SB, NBUF, CONV_TF32>(tmA, tmB, p, total_items, stream);
+        case CONV_F32OUT: return launch_halo_m<BN, MT, SB, NBUF, CONV_F32OUT>(tmA, tmB, p, total_items, stream);
         case CONV_F16_EP: return launch_halo_m<BN, MT, SB, NBUF, CONV_F16_EP>(tmA, tmB, p, total_items, stream);
         default: return launch_halo_m<BN, MT, SB, NBUF, CONV_F16>(tmA, tmB, p, total_items, stream);
     }
@@ -256,7 +250,8 @@ bool gt_conv_halo2_applicable(const ConvParams& p, int maxOH, int maxOW);
 int gt_launch_conv_halo2(const void* x, long long xs_n, long long xs_h, long long xs_w, int H, int W, const void* wpacked, int ntaps_total, ConvParams& p,
                          int ext_x, int ext_y, int maxOH, int maxOW, cudaStream_t stream);
 
-int g_conv_halo_tuning = 0;   // 0: Cout%256 -> BN 256 x 2 sub-tiles, one accumulator set; 2: BN 256 x 1 sub-tile, two sets; 3: BN 128 everywhere
+int g_conv_halo_tuning = 0;   // 0: CTA-pair kernel where applicable, else as 7; 7: single-CTA kernel (Cout%256 -> BN 256 x 2 sub-tiles, one accumulator set);
+                              // 2: single CTA, BN 256 x 1 sub-tile, two sets; 3: single CTA, BN 128 everywhere; 6: single CTA without the global stores (experiments)
 
 static void pick_tile(int Cout, int Cin, int& BN, int& MT) {
     if (Cout % 256 == 0 && g_conv_halo_tuning != 3) {
@@ -304,7 +299,9 @@ int gt_launch_conv_halo(const void* x, long long xs_n, long long xs_h, long long
     }
     p.dbg_no_store = (g_conv_halo_tuning == 6);
     GT_REQUIRE(ext_x <= 2 && ext_y <= 2, "gt_conv2d_igemm_f16 (halo): tap extent %dx%d exceeds the staged halo", ext_x, ext_y);
-    if (g_conv_halo_tuning == 5 && gt_conv_halo2_applicable(p, maxOH, maxOW))      // CTA-pair kernel (conv_igemm_halo2.cu)
+    // CTA-pair kernel (conv_igemm_halo2.cu): the default wherever it applies -- measured faster than the single-CTA kernel on every
+    // stride-1 phase (r02e: 64ch 163 -> 141 us, 128ch 112 -> 101, 256ch 105 -> 95, 512ch 114 -> 103); tuning 7 forces the single-CTA kernel
+    if (g_conv_halo_tuning != 7 && (g_conv_halo_tuning == 0 || g_conv_halo_tuning == 5) && gt_conv_halo2_applicable(p, maxOH, maxOW))
         return gt_launch_conv_halo2(x, xs_n, xs_h, xs_w, H, W, wpacked, ntaps_total, p, ext_x, ext_y, maxOH, maxOW, stream);
     p.halo_w = SUB_W * MT + ext_x;
     p.halo_h = SUB_H + ext_y;
@@ -317,9 +314,9 @@ int gt_launch_conv_halo(const void* x, long long xs_n, long long xs_h, long long
 
     gt_encode_tiled_fn encode = gt_get_encode_tiled();
     GT_REQUIRE(encode != nullptr, "gt_conv2d_igemm_f16: cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t esz = p.tf32 ? 4 : 2;
-    const int kel = p.tf32 ? 32 : 64;
-    const CUtensorMapDataType dt = p.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const cuuint64_t esz = 2;
+    const int kel = 64;
+    const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.N};

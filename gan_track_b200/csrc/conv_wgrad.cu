@@ -30,6 +30,9 @@ long long gt_wgrad_halo_workspace(int N, int UH, int UW, int UC, int SC);
 int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n, long long ss_h,
                          long long ss_w, int SH, int SW, int SC, int N, int pad, float* workspace, long long workspace_floats, cudaStream_t stream);
 static int g_wgrad_variant = 0;   // 0 = auto (halo kernel where it applies), 1 = per-tap-row kernel only
+// > 0: at most this many pixels per split-K slice.  Set (per calling thread) around the fp16x3 entry points: the tensor core's truncating
+// accumulation must stay below ~100 main-term updates per accumulator for fp32 accuracy (csrc/conv_f16x3.cu).
+thread_local int t_wgrad_px_limit = 0;
 extern "C" int gt_conv_wgrad_config(int variant) {
     const int old = g_wgrad_variant;
     g_wgrad_variant = variant;
@@ -188,18 +191,29 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const __grid_const
 }
 
 // dw[u][s][r][c] = sum over splits (in split order) of ws[split][tap][u][s]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int UC, int SC, int KW, __half* __restrict__ dw, long long ds_u,
-                                    long long ds_s, long long ds_r, long long ds_c) {
+// F32: fp16x3 route of the fp32 layers -- fp32 output, rescaled by the operands' power-of-two scales, only the first UCr x SCr channels
+// (the operands are zero padded to multiples of 64 channels)
+struct WgradOut {
+    void* dw;
+    long long ds_u, ds_s, ds_r, ds_c;
+    int f32, UCr, SCr;
+    const uint32_t *amax_u, *amax_s;
+};
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int UC, int SC, int KW, const WgradOut o) {
     const long long per = (long long)ntaps * UC * SC;
+    const float inv = o.f32 ? (1.f / gt_scale_from_amax_bits(*o.amax_u)) * (1.f / gt_scale_from_amax_bits(*o.amax_s)) : 1.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int sp = 0; sp < splits; sp++) acc += ws[sp * per + i];
         const int s = (int)(i % SC);
         long long rest = i / SC;
         const int u = (int)(rest % UC);
+        if (u >= o.UCr || s >= o.SCr) continue;
+        float acc = 0.f;
+        for (int sp = 0; sp < splits; sp++) acc += ws[sp * per + i];
         const int tap = (int)(rest / UC);
         const int r = tap / KW, c = tap - r * KW;
-        dw[u * ds_u + s * ds_s + r * ds_r + c * ds_c] = __float2half_rn(acc);
+        const long long off = u * o.ds_u + s * o.ds_s + r * o.ds_r + c * o.ds_c;
+        if (o.f32) ((float*)o.dw)[off] = acc * inv;
+        else ((__half*)o.dw)[off] = __float2half_rn(acc);
     }
 }
 
@@ -231,6 +245,11 @@ WgradPlan make_plan(int N, int UH, int UW, int UC, int SC, int ntaps) {
     pl.tap_groups = (ntaps + MAX_TG - 1) / MAX_TG;
     const int per_split = pl.u_tiles * pl.s_tiles * pl.tap_groups;
     int splits = (2 * gt_num_sms() + per_split - 1) / per_split;   // about two CTAs per SM
+    if (t_wgrad_px_limit > 0) {
+        const long long px = (long long)N * UH * UW;
+        const int need = (int)((px + t_wgrad_px_limit - 1) / t_wgrad_px_limit);
+        if (splits < need) splits = need;
+    }
     if (splits > pl.num_tiles) splits = pl.num_tiles;
     if (splits < 1) splits = 1;
     pl.splits = splits;
@@ -257,7 +276,17 @@ int launch_wgrad(const CUtensorMap& tmU, const CUtensorMap& tmS, const WgradPara
 
 }  // namespace
 
-extern "C" long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW) {
+static long long wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW);
+extern "C" long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW) { return wgrad_workspace(N, UH, UW, UC, SC, KH, KW); }
+// workspace of gt_conv2d_wgrad_f16x3 (more split-K slices than the fp16 plan: see t_wgrad_px_limit)
+constexpr int F16X3_PX_LIMIT = 4608;
+extern "C" long long gt_conv2d_wgrad_f16x3_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW) {
+    t_wgrad_px_limit = F16X3_PX_LIMIT;
+    const long long n = wgrad_workspace(N, UH, UW, UC, SC, KH, KW);
+    t_wgrad_px_limit = 0;
+    return n;
+}
+static long long wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW) {
     if (N <= 0 || UH <= 0 || UW <= 0 || UC <= 0 || SC <= 0 || KH <= 0 || KW <= 0) return 0;
     WgradPlan pl = make_plan(N, UH, UW, UC, SC, KH * KW);
     long long need = (long long)pl.splits * KH * KW * UC * SC;
@@ -268,10 +297,10 @@ extern "C" long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, in
     return need;
 }
 
-extern "C" int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n,
-                                   long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride, int pad, void* dw,
-                                   long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace, long long workspace_floats,
-                                   void* stream) {
+static int wgrad_impl(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n, long long ss_h,
+                      long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride, int pad, const WgradOut& wo, float* workspace,
+                      long long workspace_floats, void* stream) {
+    void* dw = wo.dw;
     GT_REQUIRE(u && s && dw && workspace, "gt_conv2d_wgrad_f16: null pointer");
     GT_REQUIRE(N > 0 && UH > 0 && UW > 0 && SH > 0 && SW > 0, "gt_conv2d_wgrad_f16: empty tensor");
     GT_REQUIRE(UC % 64 == 0 && SC % 64 == 0, "gt_conv2d_wgrad_f16: channel counts (%d, %d) must be multiples of 64", UC, SC);
@@ -289,7 +318,7 @@ extern "C" int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h
         const long long per = (long long)ntaps * UC * SC;
         long long g = (per + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
-        wgrad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, splits, ntaps, UC, SC, KW, (__half*)dw, ds_u, ds_s, ds_r, ds_c);
+        wgrad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, splits, ntaps, UC, SC, KW, wo);
         GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
         return GT_OK;
     }
@@ -348,7 +377,31 @@ extern "C" int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h
     const int block = 256;
     long long g = (per + block - 1) / block;
     if (g > 148 * 16) g = 148 * 16;
-    wgrad_reduce_kernel<<<(int)g, block, 0, stm>>>(workspace, pl.splits, ntaps, UC, SC, KW, (__half*)dw, ds_u, ds_s, ds_r, ds_c);
+    wgrad_reduce_kernel<<<(int)g, block, 0, stm>>>(workspace, pl.splits, ntaps, UC, SC, KW, wo);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
     return GT_OK;
+}
+
+extern "C" int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n,
+                                   long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride, int pad, void* dw,
+                                   long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace, long long workspace_floats,
+                                   void* stream) {
+    WgradOut wo = {dw, ds_u, ds_s, ds_r, ds_c, 0, UC, SC, nullptr, nullptr};
+    return wgrad_impl(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, KH, KW, stride, pad, wo, workspace, workspace_floats, stream);
+}
+
+// Weight gradient of an fp32 layer on the fp16x3 route (csrc/conv_f16x3.cu): u / s are the batch-concatenated fp16 splits
+// ([3N,H,W,UC] images (hi, hi, lo) and [3N,H,W,SC] images (hi, lo, hi), channel counts padded to multiples of 64), `N` counts all 3N
+// images, dw is fp32 and receives the first UC_real x SC_real channels rescaled by the operands' scales.
+extern "C" int gt_conv2d_wgrad_f16x3(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n,
+                                     long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride, int pad, void* dw,
+                                     long long ds_u, long long ds_s, long long ds_r, long long ds_c, int UC_real, int SC_real, const void* amax_u,
+                                     const void* amax_s, float* workspace, long long workspace_floats, void* stream) {
+    GT_REQUIRE(amax_u && amax_s, "gt_conv2d_wgrad_f16x3: null scale pointer");
+    GT_REQUIRE(UC_real >= 1 && UC_real <= UC && SC_real >= 1 && SC_real <= SC, "gt_conv2d_wgrad_f16x3: bad channel counts");
+    WgradOut wo = {dw, ds_u, ds_s, ds_r, ds_c, 1, UC_real, SC_real, (const uint32_t*)amax_u, (const uint32_t*)amax_s};
+    t_wgrad_px_limit = F16X3_PX_LIMIT;
+    const int rc = wgrad_impl(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, KH, KW, stride, pad, wo, workspace, workspace_floats, stream);
+    t_wgrad_px_limit = 0;
+    return rc;
 }

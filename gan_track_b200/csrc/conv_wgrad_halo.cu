@@ -27,6 +27,8 @@
 
 using namespace sm100;
 
+extern thread_local int t_wgrad_px_limit;      // conv_wgrad.cu: > 0 = at most this many pixels per split-K slice (fp16x3 route)
+
 namespace {
 
 constexpr int NTHREADS = 192;
@@ -177,6 +179,12 @@ WHPlan make_plan(int N, int UH, int UW, int UC, int SC) {
     const int col_tiles = pl.u_tiles * pl.s_tiles;
     int splits = gt_num_sms() / col_tiles;          // one CTA per SM (the accumulators take the whole TMEM)
     if (splits > pl.num_tiles / 4) splits = pl.num_tiles / 4;   // at least four pixel tiles per CTA to amortise the 9-tap epilogue
+    if (t_wgrad_px_limit > 0) {                     // fp16x3 route: bound the accumulator updates per split-K slice (csrc/conv_f16x3.cu)
+        const long long px = (long long)N * UH * UW;
+        const int need = (int)((px + t_wgrad_px_limit - 1) / t_wgrad_px_limit);
+        if (splits < need) splits = need;
+        if (splits > pl.num_tiles) splits = pl.num_tiles;
+    }
     if (splits < 1) splits = 1;
     pl.splits = splits;
     return pl;

@@ -95,6 +95,14 @@ template <class T> __device__ __forceinline__ void st16_stream(T* p, const Vec16
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
 
+// fp16x3 route of the fp32 convolutions (csrc/conv_f16x3.cu): power-of-two scale that maps a tensor whose max |v| has the given fp32
+// bit pattern into [2^13, 2^14); zero / non-finite maxima -> 1
+__device__ __forceinline__ float gt_scale_from_amax_bits(uint32_t bits) {
+    const int e = (int)(bits >> 23) & 0xff;
+    if (e == 0 || e == 0xff) return 1.f;
+    return __int_as_float((uint32_t)(127 + 13 - (e - 127)) << 23);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -70,32 +70,58 @@ def pack_weight(w, transpose):
     return packed
 
 
-# fp32 layers on the tensor cores as 3 x TF32.  OFF by default: measured on B200 (tools/test_tf32x3.py) the products are
-# fp32-accurate but the tensor core adds every K = 8 MMA into its fp32 accumulator with truncation, and that bias grows
-# linearly with the number of accumulator updates -- 7e-6 relative for the 64..128-channel 3x3 cases (<= 432 updates) but
-# 3e-5 .. 5e-5 for the 512-channel 3x3 layers of the fp32 blocks (1728 updates), above the 1e-5 the north star asks of fp32
-# layers (cuDNN's own fp32 kernels sit at 2e-5 there).  Needs two-level accumulation (TMEM partials promoted to fp32
-# registers every ~64 updates) before it can take over; until then those layers keep the library's true-fp32 route.
-tf32x3_enabled = False
+# fp32 layers on the tensor cores as fp16 x 3 (csrc/conv_f16x3.cu): each fp32 operand is scaled by a power of two, split into
+# hi + lo fp16 halves and the three significant products run as ONE fp16 implicit GEMM over a 3x wider channel axis with fp32
+# output, K-split by kernel row so that no stored value sees more than ~300 truncating accumulator updates; partial sums and the
+# rescale are applied in fp32.  Accuracy ~1e-6 relative (tests/test_gpu_conv_igemm.py), i.e. tighter than the library's own
+# fp32 kernels at 512 channels; True by default -- the fp32 blocks no longer call the library.
+f16x3_enabled = True
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
 
 
 def covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
-    if not (enabled and tf32x3_enabled) or x.dtype != torch.float32 or w.dtype != torch.float32 or not x.is_cuda or groups != 1:
+    if not (enabled and f16x3_enabled) or x.dtype != torch.float32 or w.dtype != torch.float32 or not x.is_cuda or groups != 1:
         return False
     if stride[0] != stride[1] or padding[0] != padding[1] or tuple(output_padding) != (0, 0) or stride[0] not in (1, 2):
         return False
     kh, kw = w.shape[2:]
     cin, cout = (w.shape[0], w.shape[1]) if transpose else (w.shape[1], w.shape[0])
-    if x.shape[1] != cin or cin % 32 != 0 or cout % 64 != 0 or kh * kw > 9 or padding[0] >= 8:
-        return False
+    if x.shape[1] != cin or kh * kw > 9 or kh > 4 or padding[0] >= 8 or cin < 16 or cout < 16:
+        return False            # 1-channel ToRGB / FromRGB have their own kernels (ops/rgb.py); tiny channel counts are not worth the padding
     if transpose and stride[0] == 2 and padding[0] != 0:
         return False
     return min(x.shape) > 0
 
 
-def igemm_forward_tf32x3(x, w, *, transpose, output_padding, stride, padding, groups):
-    """fp32 convolution / transposed convolution as ONE TF32 implicit GEMM over [x_big | x_big | x_small] x
-    [w_big | w_small | w_big] (csrc/conv_igemm.cu).  Output: fp32, channels-last."""
+def _amax(t):
+    """max|t| as an fp32 bit pattern in a device uint32 (one launch + a 4-byte memset; order independent)."""
+    lib = _lib.load()
+    out = torch.empty([1], dtype=torch.int32, device=t.device)
+    sh = list(t.shape) + [1] * (4 - t.ndim)
+    st = list(t.stride()) + [0] * (4 - t.ndim)
+    _lib.check(lib.gt_f16x3_amax(_lib.ptr(t), st[0], st[1], st[2], st[3], sh[0], sh[1], sh[2], sh[3], _lib.ptr(out), _lib.stream_of(t)), 'gt_f16x3_amax')
+    _lib.count_launch()
+    return out
+
+
+def _split_act(t, layout, amax):
+    """fp32 [N,C,H,W] (any strides) -> the fp16 hi / lo operand layouts of csrc/conv_f16x3.cu; returns (tensor, Cp)."""
+    lib = _lib.load()
+    N, C, H, W = t.shape
+    cp = _pad64(C)
+    out = torch.empty([N, H, W, 3 * cp] if layout == 0 else [3 * N, H, W, cp], dtype=torch.float16, device=t.device)
+    s = t.stride()
+    _lib.check(lib.gt_f16x3_split_act(_lib.ptr(t), s[0], s[1], s[2], s[3], N, C, H, W, cp, layout, _lib.ptr(amax), _lib.ptr(out), _lib.stream_of(t)),
+               'gt_f16x3_split_act')
+    _lib.count_launch()
+    return out, cp
+
+
+def igemm_forward_f16x3(x, w, *, transpose, output_padding, stride, padding, groups):
+    """fp32 convolution / transposed convolution on the fp16 tensor-core kernels (fp16 x 3).  Output: fp32, channels-last."""
     lib = _lib.load()
     N, cin, H, W = x.shape
     kh, kw = w.shape[2:]
@@ -103,31 +129,70 @@ def igemm_forward_tf32x3(x, w, *, transpose, output_padding, stride, padding, gr
     OH, OW = out_size(H, W, kh, kw, stride[0], padding[0], transpose)
     if OH <= 0 or OW <= 0:
         return None
+    _log('fwd32', N, cin, cout, H, W, kh, stride[0], transpose)
     with torch.cuda.device(x.device):
         st = _lib.stream_of(x)
-        xs = torch.empty([N, H, W, 3 * cin], dtype=torch.float32, device=x.device)
-        sx = x.stride()
-        _lib.check(lib.gt_split_tf32x3(_lib.ptr(x), sx[0], sx[1], sx[2], sx[3], N, cin, H, W, _lib.ptr(xs), st), 'gt_split_tf32x3')
+        ax, aw = _amax(x), _amax(w)
+        xs, cinp = _split_act(x, 0, ax)
+        coutp = _pad64(cout)
         sw = w.stride()
         s_co, s_ci = (sw[1], sw[0]) if transpose else (sw[0], sw[1])
-        wp = torch.empty([kh * kw, cout, 3 * cin], dtype=torch.float32, device=x.device)
-        _lib.check(lib.gt_conv_pack_weight_tf32x3(_lib.ptr(w), s_co, s_ci, sw[2], sw[3], cout, cin, kh, kw, _lib.ptr(wp), st), 'gt_conv_pack_weight_tf32x3')
-        y = torch.empty([N, cout, OH, OW], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-        if y.stride(1) != 1 or y.stride(3) != cout:            # size-1 dims can leave ambiguous strides; force NHWC
-            y = torch.empty([N, OH, OW, cout], dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
-        c3 = 3 * cin
-        _lib.check(lib.gt_conv2d_igemm_tf32(_lib.ptr(xs), H * W * c3, W * c3, c3, _lib.ptr(wp), _lib.ptr(y), OH * OW * cout, OW * cout, cout,
-                                            N, H, W, c3, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0, st),
-                   'gt_conv2d_igemm_tf32')
+        wp = torch.empty([kh * kw, coutp, 3 * cinp], dtype=torch.float16, device=x.device)
+        _lib.check(lib.gt_f16x3_pack_weight(_lib.ptr(w), s_co, s_ci, sw[2], sw[3], cout, cin, kh, kw, coutp, cinp, _lib.ptr(aw), _lib.ptr(wp), st),
+                   'gt_f16x3_pack_weight')
+        # K-split: one partial sum per kernel row for stride-1 / strided kernels with several rows; the four parity phases of the
+        # transposed stride-2 form are short already (<= 4 taps each)
+        nslabs = kh if (kh > 1 and not (transpose and stride[0] == 2)) else 1
+        slab = N * OH * OW * coutp
+        part = torch.empty([nslabs, N, OH, OW, coutp], dtype=torch.float32, device=x.device)
+        c3 = 3 * cinp
+        _lib.check(lib.gt_conv2d_igemm_f16_f32out(_lib.ptr(xs), H * W * c3, W * c3, c3, _lib.ptr(wp), _lib.ptr(part), OH * OW * coutp, OW * coutp, coutp,
+                                                  N, H, W, c3, OH, OW, coutp, kh, kw, stride[0], padding[0], 1 if transpose else 0,
+                                                  slab if nslabs > 1 else 0, st), 'gt_conv2d_igemm_f16_f32out')
+        y = torch.empty([N, OH, OW, cout], dtype=torch.float32, device=x.device)
+        _lib.check(lib.gt_f16x3_slab_reduce(_lib.ptr(part), slab, nslabs, N * OH * OW, coutp, cout, _lib.ptr(ax), _lib.ptr(aw), _lib.ptr(y), st),
+                   'gt_f16x3_slab_reduce')
         _lib.count_launch(3)
-    return y
+    return y.permute(0, 3, 1, 2)
+
+
+def igemm_wgrad_f16x3(dy, x, weight_shape, *, transpose, output_padding, stride, padding, groups):
+    """Weight gradient of an fp32 layer on the fp16 x 3 route: batch-concatenated hi / lo splits through the fp16 wgrad kernels."""
+    kh, kw = weight_shape[2:]
+    if not (enabled and f16x3_enabled) or dy.dtype != torch.float32 or x.dtype != torch.float32 or not x.is_cuda or groups != 1:
+        return None
+    if stride[0] != stride[1] or padding[0] != padding[1] or stride[0] not in (1, 2) or kh * kw > 9 or padding[0] >= 8:
+        return None
+    u, s = (x, dy) if transpose else (dy, x)
+    if u.shape[1] != weight_shape[0] or s.shape[1] != weight_shape[1] or u.shape[1] < 16 or s.shape[1] < 16:
+        return None
+    if min(u.shape) == 0 or min(s.shape) == 0:
+        return None
+    lib = _lib.load()
+    N, UC, UH, UW = u.shape
+    _, SC, SH, SW = s.shape
+    _log('wgrad32', N, SC, UC, SH, SW, kh, stride[0], transpose)
+    with torch.cuda.device(x.device):
+        au, as_ = _amax(u), _amax(s)
+        us, ucp = _split_act(u, 1, au)
+        ss, scp = _split_act(s, 2, as_)
+        n3 = 3 * N
+        nws = lib.gt_conv2d_wgrad_f16x3_workspace(n3, UH, UW, ucp, scp, kh, kw)
+        ws = torch.empty([nws], dtype=torch.float32, device=x.device)
+        dw = torch.empty(list(weight_shape), dtype=torch.float32, device=x.device)
+        d = dw.stride()
+        _lib.check(lib.gt_conv2d_wgrad_f16x3(_lib.ptr(us), UH * UW * ucp, UW * ucp, ucp, UH, UW, ucp, _lib.ptr(ss), SH * SW * scp, SW * scp, scp, SH, SW, scp,
+                                             n3, kh, kw, stride[0], padding[0], _lib.ptr(dw), d[0], d[1], d[2], d[3], UC, SC, _lib.ptr(au), _lib.ptr(as_),
+                                             _lib.ptr(ws), nws, _lib.stream_of(x)), 'gt_conv2d_wgrad_f16x3')
+        _lib.count_launch(2)
+    return dw
 
 
 def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, packed=None, epilogue=None):
     """epilogue: None, or (bias fp16 [Cout] or None, act code 1 / 3, alpha, gain, clamp) -- the layer's bias_act fused into
     the kernel's epilogue (fp16 only; the caller checks `covered` first)."""
     if epilogue is None and covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
-        return igemm_forward_tf32x3(x, w, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
+        return igemm_forward_f16x3(x, w, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
     if not covered(x, w, transpose, output_padding, stride, padding, groups):
         return None
     lib = _lib.load()
@@ -159,6 +224,8 @@ def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, p
 
 def igemm_wgrad(dy, x, weight_shape, *, transpose, output_padding, stride, padding, groups):
     kh, kw = weight_shape[2:]
+    if dy.dtype == torch.float32 and x.dtype == torch.float32:
+        return igemm_wgrad_f16x3(dy, x, weight_shape, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
     if not enabled or dy.dtype != torch.float16 or x.dtype != torch.float16 or not x.is_cuda or groups != 1:
         return None
     if stride[0] != stride[1] or padding[0] != padding[1] or stride[0] not in (1, 2) or kh * kw > 9 or padding[0] >= 8:

@@ -35,10 +35,19 @@ def _layout(channels_last):
     return torch.channels_last if channels_last else torch.contiguous_format
 
 
-def _working_type(use_fp16, channels_last, force_fp32):
-    """(dtype, memory_format) a block computes in: fp16 (+ channels-last) unless forced to fp32."""
-    half = use_fp16 and not force_fp32
-    return (torch.float16 if half else torch.float32), _layout(channels_last and not force_fp32)
+# fp32 blocks on a CUDA device also compute channels-last: their convolutions run on the NHWC tensor-core kernels (fp16 x 3 route,
+# ops/conv_igemm.py) and the fused modulation / activation kernels take dense NHWC tensors.  Results are layout independent.
+fp32_channels_last = True
+
+
+def _working_type(use_fp16, channels_last, force_fp32, on_cuda=True):
+    """(dtype, memory_format) a block computes in: fp16 (+ channels-last) unless forced to fp32 or off the GPU."""
+    half = use_fp16 and not force_fp32 and on_cuda
+    if not on_cuda:
+        return torch.float32, torch.contiguous_format
+    if half:
+        return torch.float16, _layout(channels_last)
+    return torch.float32, _layout(fp32_channels_last)
 
 
 def _conv_weight(out_channels, in_channels, kernel_size, channels_last):
@@ -357,7 +366,7 @@ class SynthesisBlock(torch.nn.Module):
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, **layer_kwargs):
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
         styles = iter(ws.unbind(dim=1))
-        dtype, memory_format = _working_type(self.use_fp16, self.channels_last, force_fp32 or ws.device.type != 'cuda')
+        dtype, memory_format = _working_type(self.use_fp16, self.channels_last, force_fp32, ws.device.type == 'cuda')
         fused = self.fused_modconv_default if fused_modconv is None else fused_modconv
         if fused == 'inference_only':
             fused = not self.training
@@ -471,7 +480,7 @@ class DiscriminatorBlock(torch.nn.Module):
 
     def forward(self, x, img, force_fp32=False):
         on_cuda = (img if x is None else x).device.type == 'cuda'
-        dtype, memory_format = _working_type(self.use_fp16, self.channels_last, force_fp32 or not on_cuda)
+        dtype, memory_format = _working_type(self.use_fp16, self.channels_last, force_fp32, on_cuda)
         square = [self.resolution, self.resolution]
         if x is not None:
             misc.assert_shape(x, [None, self.in_channels, *square])

@@ -102,21 +102,34 @@ int gt_conv2d_igemm_f16_bias_act(const void* x, long long xs_n, long long xs_h, 
                                  int KH, int KW, int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain,
                                  float clamp, void* stream);
 
-/* ---- fp32 convolutions on the tensor cores (3 x TF32) ------------------------------------------------------------------
- * For the fp32 blocks of the networks (true-fp32 accuracy required; the reference runs them on cuDNN with TF32 off,
- * S3/training/training_loop_mi_multimodal.py:169-170).  Each fp32 value v is split into big = rna_tf32(v) and
- * small = rna_tf32(v - big); x*w ~= xb*wb + xb*ws + xs*wb is ONE TF32 convolution over a 3x wider channel dimension:
- *   gt_split_tf32x3:             x [N,C,H,W] (any element strides)  -> out [N,H,W,3C] = [big | big | small]
- *   gt_conv_pack_weight_tf32x3:  w (strided, like gt_conv_pack_weight_f16) -> out [KH*KW][Cout][3*Cin] = [big | small | big]
- *   gt_conv2d_igemm_tf32:        same contract as gt_conv2d_igemm_f16 with fp32 tensors consumed as TF32 (Cin a multiple
- *                                of 32 -- pass 3*C -- fp32 NHWC output); same kernels, kind::tf32. */
-int gt_split_tf32x3(const void* x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C, int H, int W, void* out,
-                    void* stream);
-int gt_conv_pack_weight_tf32x3(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin, int KH,
-                               int KW, void* out, void* stream);
-int gt_conv2d_igemm_tf32(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
-                         long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
-                         int stride, int pad, int transposed, void* stream);
+/* ---- fp32 convolutions on the tensor cores (fp16 x 3) -------------------------------------------------------------------
+ * For the fp32 blocks of the networks (true-fp32 accuracy required; the reference runs them on the library with TF32 off,
+ * S3/training/networks_stylegan2.py:486, 756; S3/training/training_loop_mi_multimodal.py:169-170; call site
+ * OPS/conv2d_gradfix.py:37-45).  Every fp32 tensor v is scaled by a power of two taken from max|v| and split into
+ * hi = fp16(v s), lo = fp16(v s - hi); x*w ~= (xh*wh + xh*wl + xl*wh) / (s_x s_w) is ONE fp16 convolution over a 3x wider
+ * channel axis with fp32 output, K-split by kernel row into partial sums that are added in fp32 (csrc/conv_f16x3.cu):
+ *   gt_f16x3_amax:         max|v| of a tensor of up to 4 dims (element strides) as an fp32 bit pattern in `amax_bits` (uint32, device)
+ *   gt_f16x3_split_act:    x [N,C,H,W] (any element strides) -> fp16, channels padded to Cp (multiple of 64, zero filled):
+ *                          layout 0: [N,H,W,3*Cp] = [hi | hi | lo]            (operand of the forward / data-gradient kernel)
+ *                          layout 1: [3N,H,W,Cp], images (hi, hi, lo)          (U operand of the weight-gradient kernel)
+ *                          layout 2: [3N,H,W,Cp], images (hi, lo, hi)          (S operand)
+ *   gt_f16x3_pack_weight:  w (strided, like gt_conv_pack_weight_f16) -> [KH*KW][Coutp][3*Cinp] = [hi | lo | hi], zero padded
+ *   gt_conv2d_igemm_f16_f32out: contract of gt_conv2d_igemm_f16 with fp32 NHWC output (raw accumulators); with slab_stride > 0
+ *                          and KH > 1 one partial sum per kernel row at y + row * slab_stride elements
+ *   gt_f16x3_slab_reduce:  y[rows][C] = (sum over nslabs of slabs[s][rows][Cp], first C columns) / (s_a s_b)
+ *   gt_conv2d_wgrad_f16x3: contract of gt_conv2d_wgrad_f16 on the batch-concatenated splits (N counts all 3N images), fp32 dw,
+ *                          only the first UC_real x SC_real channels written, rescaled by 1 / (s_u s_s) */
+int gt_f16x3_amax(const void* x, long long s0, long long s1, long long s2, long long s3, int d0, int d1, int d2, int d3, void* amax_bits,
+                  void* stream);
+int gt_f16x3_split_act(const void* x, long long s_n, long long s_c, long long s_h, long long s_w, int N, int C, int H, int W, int Cp,
+                       int layout, const void* amax_bits, void* out, void* stream);
+int gt_f16x3_pack_weight(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin, int KH, int KW,
+                         int Coutp, int Cinp, const void* amax_bits, void* out, void* stream);
+int gt_conv2d_igemm_f16_f32out(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                               long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
+                               int stride, int pad, int transposed, long long slab_stride, void* stream);
+int gt_f16x3_slab_reduce(const void* slabs, long long slab_stride, int nslabs, long long rows, int Cp, int C, const void* amax_a,
+                         const void* amax_b, void* y, void* stream);
 
 /* Weight gradient of the same convolutions (replaces cuDNN wgrad reached through autograd of F.conv2d /
  * F.conv_transpose2d, OPS/conv2d_gradfix.py:37-45).  U is the operand walked pixel by pixel, S the operand read at
@@ -134,6 +147,11 @@ int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long
                         long long ss_n, long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride,
                         int pad, void* dw, long long ds_u, long long ds_s, long long ds_r, long long ds_c, float* workspace,
                         long long workspace_floats, void* stream);
+long long gt_conv2d_wgrad_f16x3_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW);
+int gt_conv2d_wgrad_f16x3(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s,
+                          long long ss_n, long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride,
+                          int pad, void* dw, long long ds_u, long long ds_s, long long ds_r, long long ds_c, int UC_real, int SC_real,
+                          const void* amax_u, const void* amax_s, float* workspace, long long workspace_floats, void* stream);
 
 /* ---- fully-connected layers at training batch sizes (fp32, 1 <= M <= 64 rows) ----------------------------------------
  * Replace `w = weight * weight_gain; b = bias * bias_gain; addmm(b, x, w.t())` of FullyConnectedLayer.forward

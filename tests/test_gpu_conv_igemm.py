@@ -126,55 +126,50 @@ def test_conv_backend_routes_fp16_path_shapes_to_igemm():
     assert conv_backend.stats['library'] == before['library']
 
 
-# fp32 layers on the tensor cores as 3 x TF32 (csrc/conv_igemm.cu: gt_split_tf32x3, gt_conv_pack_weight_tf32x3, gt_conv2d_igemm_tf32)
+# fp32 layers on the tensor cores as fp16 x 3 (csrc/conv_f16x3.cu + the fp32-output mode of the implicit-GEMM kernels)
 FP32_CASES = [
     ('fp32_3x3_p1_512_512_4', 8, 512, 512, 4, 4, 3, 1, 1, False),
     ('fp32_3x3_p1_512_512_16', 4, 512, 512, 16, 16, 3, 1, 1, False),
+    ('fp32_3x3_p1_513_512_4', 8, 513, 512, 4, 4, 3, 1, 1, False),           # the convolution after the minibatch-std layer (D b4)
     ('fp32_3x3_p1_64_128_19', 3, 64, 128, 19, 19, 3, 1, 1, False),
     ('fp32_3x3_T_s2_512_512_8', 4, 512, 512, 8, 8, 3, 2, 0, True),
+    ('fp32_3x3_s2_512_512_17', 4, 512, 512, 17, 17, 3, 2, 0, False),
     ('fp32_3x3_s2_128_64_17', 3, 128, 64, 17, 17, 3, 2, 0, False),
-    ('fp32_1x1_128_64_8', 5, 128, 64, 8, 8, 1, 1, 0, False),
+    ('fp32_1x1_512_512_8', 5, 512, 512, 8, 8, 1, 1, 0, False),
     ('fp32_3x3_T_s1_p1_32_64_16', 2, 32, 64, 16, 16, 3, 1, 1, True),
+    ('fp32_3x3_p1_40_72_9', 2, 40, 72, 9, 9, 3, 1, 1, False),               # ragged channel counts (padded to 64 / 128 inside)
 ]
 
 
+@pytest.mark.parametrize('scale', [1.0, 1e-6, 3e3], ids=['unit', 'tiny', 'large'])
 @pytest.mark.parametrize('case', FP32_CASES, ids=lambda c: c[0])
-def test_fp32_conv_3xtf32_accuracy(case):
-    """The opt-in 3 x TF32 route for fp32 layers against a float64 reference.  Products are fp32-accurate; what remains is the
-    tensor core's truncating fp32 accumulation, linear in the number of K = 8 accumulator updates (taps * 3 * Cin / 8):
-    <= 1e-5 relative (the north star's fp32 bound) up to ~450 updates, <= 1e-4 for the 512-channel 3x3 layers -- which is why
-    the route is OFF by default (conv_igemm.tf32x3_enabled) and those layers keep the library's true-fp32 kernels."""
-    from gan_track_b200.torch_utils.ops import conv2d_gradfix, conv_backend, conv_igemm
+def test_fp32_conv_f16x3_accuracy(case, scale):
+    """fp32 layers on the tensor cores (fp16 x 3 with power-of-two scaling, K-split partial sums) against a float64 reference: forward,
+    data gradient and weight gradient within the north star's 1e-5 (fp32), for unit-scale tensors, for tiny gradients (1e-6: the
+    second-order passes) and for large activations; no call may reach the library."""
+    from gan_track_b200.torch_utils.ops import conv2d_gradfix, conv_backend
     _, N, ci, co, H, W, k, s, p, tr = case
     g = torch.Generator(device='cuda').manual_seed(5)
-    x = torch.randn([N, ci, H, W], device='cuda', generator=g).requires_grad_(True)
+    x = (torch.randn([N, ci, H, W], device='cuda', generator=g) * scale).requires_grad_(True)
     wshape = [ci, co, k, k] if tr else [co, ci, k, k]
     w = (torch.randn(wshape, device='cuda', generator=g) / (ci * k * k) ** 0.5).requires_grad_(True)
     fn = conv2d_gradfix.conv_transpose2d if tr else conv2d_gradfix.conv2d
     before = dict(conv_backend.stats)
-    y0 = fn(x, w, stride=s, padding=p)
-    assert conv_backend.stats['library'] - before['library'] == 1, 'fp32 layers take the library route by default'
-    old_flag = conv_igemm.tf32x3_enabled
-    conv_igemm.tf32x3_enabled = True
-    try:
-        before = dict(conv_backend.stats)
-        y = fn(x, w, stride=s, padding=p)
-        dy = torch.randn(y.shape, device='cuda', generator=g)
-        dx, = torch.autograd.grad(y, [x], dy)
-        assert conv_backend.stats['igemm'] - before['igemm'] >= 1, 'the forward pass must take the tensor-core route (the data gradient too where its channel counts allow)'
-    finally:
-        conv_igemm.tf32x3_enabled = old_flag
-    xr, wr = x.detach().double().requires_grad_(True), w.detach().double()
+    y = fn(x, w, stride=s, padding=p)
+    dy = torch.randn(y.shape, device='cuda', generator=g) * scale
+    dx, dw = torch.autograd.grad(y, [x, w], dy)
+    used = {k_: conv_backend.stats[k_] - before[k_] for k_ in before}
+    assert used['library'] == 0 and used['library_wgrad'] == 0 and used['igemm'] == 2 and used['igemm_wgrad'] == 1, used
+    xr, wr = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
     ref = F.conv_transpose2d(xr, wr, stride=s, padding=p) if tr else F.conv2d(xr, wr, stride=s, padding=p)
-    rdx, = torch.autograd.grad(ref, [xr], dy.double())
-    updates = k * k * 3 * max(ci, co) // 8
-    tol = 1e-5 if updates <= 450 else 1e-4
-    assert y.dtype == torch.float32 and y.shape == ref.shape
+    rdx, rdw = torch.autograd.grad(ref, [xr, wr], dy.double())
+    assert y.dtype == torch.float32 and y.shape == ref.shape and dw.shape == w.shape and dw.dtype == torch.float32
 
     def rel64(a, b):
         return float((a.detach().double() - b.detach()).abs().max() / b.detach().abs().max())
-    assert rel64(y, ref) <= tol and rel64(dx, rdx) <= tol
-    assert rel64(y0, ref) <= 1e-4
+    errs = (rel64(y, ref), rel64(dx, rdx), rel64(dw, rdw))
+    print(f'\n  f16x3 {case[0]} scale {scale:g}: y {errs[0]:.1e} dx {errs[1]:.1e} dw {errs[2]:.1e}')
+    assert max(errs) <= 1e-5, errs
 
 
 @pytest.mark.parametrize('act,gain,clamp,bias', [('lrelu', None, 256.0, True), ('lrelu', 0.7, 0.5, True), ('linear', 0.7071, 181.0, True), ('linear', None, None, False)])

@@ -146,16 +146,16 @@ if args.time and fails == 0:
         kw_ = dict(transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1)
         t_full = bench(lambda: conv_igemm.igemm_forward(x, w, **kw_))
         res = {}
-        for v in (0, 2, 3, 1, 5):
+        for v in (0, 2, 3, 1, 7):
             _lib.load().gt_conv_igemm_config(v)
             res[v] = bench(lambda: conv_igemm.igemm_forward(x, w, packed=pk, **kw_))
         _lib.load().gt_conv_igemm_config(args.variant)
-        t_ours, t_v2, t_v3, t_v1, t_v5 = res[0], res[2], res[3], res[1], res[5]
+        t_ours, t_v2, t_v3, t_v1, t_v5 = res[0], res[2], res[3], res[1], res[7]
         if tr:
             t_lib = bench(lambda: F.conv_transpose2d(x, w, stride=s, padding=p))
         else:
             t_lib = bench(lambda: F.conv2d(x, w, stride=s, padding=p))
-        line = f'{name:40s} fwd ours {t_ours * 1e3:7.1f} us {flops / t_ours / 1e9:6.0f} TF/s (+pack {t_full * 1e3:6.1f}; per-tap {t_v1 * 1e3:6.1f}, cfg2 {t_v2 * 1e3:6.1f}, cfg3 {t_v3 * 1e3:6.1f}, CTA-pair {t_v5 * 1e3:6.1f}) | cudnn {t_lib * 1e3:7.1f} us {flops / t_lib / 1e9:6.0f} TF/s'
+        line = f'{name:40s} fwd ours {t_ours * 1e3:7.1f} us {flops / t_ours / 1e9:6.0f} TF/s (+pack {t_full * 1e3:6.1f}; per-tap {t_v1 * 1e3:6.1f}, cfg2 {t_v2 * 1e3:6.1f}, cfg3 {t_v3 * 1e3:6.1f}, single-CTA {t_v5 * 1e3:6.1f}) | cudnn {t_lib * 1e3:7.1f} us {flops / t_lib / 1e9:6.0f} TF/s'
         if args.wgrad:
             dy = torch.randn([N, co, OH, OW], device=dev).to(torch.float16).contiguous(memory_format=torch.channels_last)
             t_w = bench(lambda: conv_igemm.igemm_wgrad(dy, x, tuple(wshape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1))
