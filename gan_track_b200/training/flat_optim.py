@@ -19,9 +19,13 @@ class FlatParams:
         self.params = list(module.parameters())
         assert self.params and all(p.dtype == torch.float32 and p.is_cuda for p in self.params)
         self.sizes = [p.numel() for p in self.params]
-        self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+        # every parameter starts on a 256-byte boundary: kernels read parameters (biases, weights) with 16-byte vector loads and
+        # bulk copies, which the views into this buffer must allow like separately allocated tensors do
+        ALIGN = 64
+        padded = [(n + ALIGN - 1) // ALIGN * ALIGN for n in self.sizes]
+        self.offsets = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
         self.total = int(self.offsets[-1])
-        self.flat = torch.empty([self.total], dtype=torch.float32, device=self.params[0].device)
+        self.flat = torch.zeros([self.total], dtype=torch.float32, device=self.params[0].device)
         with torch.no_grad():
             for p, off, n in zip(self.params, self.offsets[:-1], self.sizes):
                 view = self.flat[int(off):int(off) + n].view(p.shape)

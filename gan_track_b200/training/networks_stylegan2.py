@@ -374,7 +374,7 @@ class SynthesisBlock(torch.nn.Module):
         conv = dict(fused_modconv=fused, **layer_kwargs)
 
         if self.in_channels == 0:
-            x = self.const.to(dtype=dtype, memory_format=memory_format).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
+            x = self.const.to(dtype=dtype).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous(memory_format=memory_format)
             x = self.conv1(x, next(styles), **conv)
         else:
             misc.assert_shape(x, [None, self.in_channels, half_res, half_res])
