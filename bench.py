@@ -262,8 +262,8 @@ def hot_kernel_rooflines(device, pk):
                          peak_source=pk['src'], ms_per_launch=ms, **extra)
 
     cfg = dict(output_padding=(0, 0), groups=1, stride=(1, 1), padding=(1, 1))
-    for ci, co, r, tag in [(512, 512, 32, 'conv_igemm_halo_kernel<256,2,4,1>'), (256, 256, 64, 'conv_igemm_halo_kernel<256,1,5,2>'),
-                           (128, 128, 128, 'conv_igemm_halo_kernel<128,2,6,2>'), (64, 64, 256, 'conv_igemm_halo_kernel<64,4,6,2>')]:
+    for ci, co, r, tag in [(512, 512, 32, 'conv_igemm_halo2_kernel<256,1,10> (CTA pair)'), (256, 256, 64, 'conv_igemm_halo2_kernel<256,1,10> (CTA pair)'),
+                           (128, 128, 128, 'conv_igemm_halo2_kernel<128,2,12> (CTA pair)'), (64, 64, 256, 'conv_igemm_halo2_kernel<64,4,10> (CTA pair)')]:
         xs = rot(lambda: t16([32, ci, r, r]), 32 * ci * r * r * 2 * 2)
         w = (torch.randn([co, ci, 3, 3], device=device) / (ci * 9) ** 0.5).to(torch.float16)
         pkd = conv_igemm.pack_weight(w, False)

@@ -46,6 +46,90 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
+// dense tensors (any permutation of a contiguous block): the maximum does not care about the order -> flat 16-byte loads
+__global__ void __launch_bounds__(256) amax_dense_kernel(const float* __restrict__ x, long long n, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    const long long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x4[i];
+        const uint32_t a = __float_as_uint(v.x) & 0x7fffffffu, b = __float_as_uint(v.y) & 0x7fffffffu, c = __float_as_uint(v.z) & 0x7fffffffu,
+                       d = __float_as_uint(v.w) & 0x7fffffffu;
+        m = max(max(m, max(a, b)), max(c, d));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = max(m, __float_as_uint(x[(n4 << 2) + threadIdx.x]) & 0x7fffffffu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ uint32_t sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) m = max(m, sm[w]);
+        if (m) atomicMax(out, m);
+    }
+}
+
+// fast path of split_act_kernel: x dense channels-last (s_c == 1), C == Cp a multiple of 8: one thread = 8 channels of one pixel
+__global__ void __launch_bounds__(256) split_act_nhwc8_kernel(const float* __restrict__ x, uint32_t npix, uint32_t c8n, uint32_t pix_per_img, int N, int layout,
+                                                              const uint32_t* __restrict__ amax, __half* __restrict__ out) {
+    const float sc = gt_scale_from_amax_bits(*amax);
+    const uint32_t total = npix * c8n;
+    const uint32_t Cp = c8n * 8;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t pix = i / c8n, c = (i - pix * c8n) * 8;
+        const float4 a = *reinterpret_cast<const float4*>(x + (size_t)pix * Cp + c), b = *reinterpret_cast<const float4*>(x + (size_t)pix * Cp + c + 4);
+        const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            hi[k] = __float2half_rn(v[k]);
+            lo[k] = __float2half_rn(v[k] - __half2float(hi[k]));
+        }
+        const uint4 H = *reinterpret_cast<const uint4*>(hi), L = *reinterpret_cast<const uint4*>(lo);
+        if (layout == 0) {
+            __half* o = out + (size_t)pix * (3 * Cp) + c;
+            *reinterpret_cast<uint4*>(o) = H;
+            *reinterpret_cast<uint4*>(o + Cp) = L;
+            *reinterpret_cast<uint4*>(o + 2 * Cp) = H;
+        } else {
+            __half* o = out + (size_t)pix * Cp + c;
+            const size_t plane = (size_t)N * pix_per_img * Cp;
+            *reinterpret_cast<uint4*>(o) = layout == 1 ? H : L;
+            *reinterpret_cast<uint4*>(o + plane) = layout == 1 ? L : H;
+            *reinterpret_cast<uint4*>(o + 2 * plane) = H;
+        }
+    }
+}
+
+// fast path of pack_weight_kernel for kernels of up to 9 taps: one thread = one (co, ci) pair, all taps (its taps are KH*KW consecutive
+// floats when the weight is contiguous)
+__global__ void __launch_bounds__(256) pack_weight_pair_kernel(const float* __restrict__ w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout,
+                                                               int Cin, int KH, int KW, int Coutp, int Cinp, const uint32_t* __restrict__ amax,
+                                                               __half* __restrict__ out) {
+    const float sc = gt_scale_from_amax_bits(*amax);
+    const uint32_t total = (uint32_t)Coutp * (uint32_t)Cinp;
+    const __half z = __float2half_rn(0.f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t co = i / (uint32_t)Cinp, ci = i - co * (uint32_t)Cinp;
+        const bool live = ci < (uint32_t)Cin && co < (uint32_t)Cout;
+        const float* wp = w + (long long)co * s_co + (long long)ci * s_ci;
+        for (int r = 0; r < KH; r++)
+            for (int q = 0; q < KW; q++) {
+                __half hi = z, lo = z;
+                if (live) {
+                    const float v = wp[r * s_r + q * s_s] * sc;
+                    hi = __float2half_rn(v);
+                    lo = __float2half_rn(v - __half2float(hi));
+                }
+                __half* o = out + ((size_t)(r * KW + q) * Coutp + co) * (3ull * Cinp) + ci;
+                o[0] = lo;
+                o[Cinp] = hi;
+                o[2 * Cinp] = hi;
+            }
+    }
+}
+
 // activations: x [N,C,H,W] (element strides) -> out fp16.
 //   layout 0 (channel concat, operand of the forward / data-gradient kernels): out[n][h][w][3*Cp] = [hi | lo | hi]
 //   layout 1 (batch concat, U operand of the weight-gradient kernels):         out[3N][h][w][Cp], images (hi, lo, hi)
@@ -85,29 +169,7 @@ __global__ void __launch_bounds__(256) split_act_kernel(const float* __restrict_
     }
 }
 
-// weights: w[co * s_co + ci * s_ci + r * s_r + s * s_s] -> out[t][Coutp][3*Cinp] = [lo | hi | hi], zero padded
-__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout,
-                                                          int Cin, int KH, int KW, int Coutp, int Cinp, const uint32_t* __restrict__ amax, __half* __restrict__ out) {
-    const float sc = gt_scale_from_amax_bits(*amax);
-    const long long total = (long long)KH * KW * Coutp * Cinp;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ci = (int)(i % Cinp);
-        long long r_ = i / Cinp;
-        const int co = (int)(r_ % Coutp);
-        const int t = (int)(r_ / Coutp);
-        const int r = t / KW, s = t - r * KW;
-        __half hi = __float2half_rn(0.f), lo = hi;
-        if (ci < Cin && co < Cout) {
-            const float v = w[co * s_co + ci * s_ci + r * s_r + s * s_s] * sc;
-            hi = __float2half_rn(v);
-            lo = __float2half_rn(v - __half2float(hi));
-        }
-        __half* o = out + ((long long)t * Coutp + co) * (3ll * Cinp) + ci;
-        o[0] = lo;
-        o[Cinp] = hi;
-        o[2 * Cinp] = hi;
-    }
-}
+// weights: w[co * s_co + ci * s_ci + r * s_r + s * s_s] -> out[t][Coutp][3*Cinp] = [lo | hi | hi], zero padded: pack_weight_pair_kernel above
 
 // y[i] = (sum_s slab[s][i]) / (scale_a * scale_b), i over a dense [rows][Cp] fp32 array of which the first C columns are kept:
 // y is [rows][C] dense (the NHWC output of the convolution)
@@ -169,7 +231,34 @@ extern "C" int gt_f16x3_amax(const void* x, long long s0, long long s1, long lon
         return GT_ERR_CUDA;
     }
     const long long total = (long long)d0 * d1 * d2 * d3;
-    amax_kernel<<<grid_for(total), 256, 0, st>>>((const float*)x, s0, s1, s2, s3, d1, d2, d3, total, (uint32_t*)amax_bits);
+    // dense in some dimension order (strides are a permutation of a contiguous layout) and 16-byte aligned: flat vector loads
+    bool dense = ((uintptr_t)x & 15) == 0;
+    {
+        long long st_[4] = {s0, s1, s2, s3};
+        int dm[4] = {d0, d1, d2, d3};
+        long long expect = 1;
+        bool used[4] = {false, false, false, false};
+        for (int k = 0; k < 4 && dense; k++) {
+            int pick = -1;
+            for (int j = 0; j < 4; j++)
+                if (!used[j] && (dm[j] == 1 || st_[j] == expect)) {
+                    if (pick < 0 || dm[j] == 1) pick = j;
+                }
+            if (pick < 0) dense = false;
+            else {
+                used[pick] = true;
+                expect *= dm[pick];
+            }
+        }
+    }
+    if (dense) {
+        long long g = (total / 4 + 255) / 256;
+        const long long cap = (long long)gt_num_sms() * 8;
+        if (g > cap) g = cap;
+        if (g < 1) g = 1;
+        amax_dense_kernel<<<(int)g, 256, 0, st>>>((const float*)x, total, (uint32_t*)amax_bits);
+    } else
+        amax_kernel<<<grid_for(total), 256, 0, st>>>((const float*)x, s0, s1, s2, s3, d1, d2, d3, total, (uint32_t*)amax_bits);
     GT_CUDA_LAUNCH_CHECK("gt_f16x3_amax");
     return GT_OK;
 }
@@ -180,6 +269,13 @@ extern "C" int gt_f16x3_split_act(const void* x, long long s_n, long long s_c, l
     GT_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 64 == 0, "gt_f16x3_split_act: bad shape (C %d, padded %d)", C, Cp);
     GT_REQUIRE(layout >= 0 && layout <= 2, "gt_f16x3_split_act: layout must be 0 (channel concat), 1 (batch concat, U role) or 2 (batch concat, S role)");
     const long long total = (long long)N * H * W * Cp;
+    if (C == Cp && s_c == 1 && s_w == C && s_h == (long long)W * C && s_n == (long long)H * W * C && ((uintptr_t)x & 15) == 0 && total < (1ll << 31)) {
+        const uint32_t npix = (uint32_t)(N * H * W), c8n = (uint32_t)(Cp / 8);
+        split_act_nhwc8_kernel<<<grid_for(total / 8), 256, 0, (cudaStream_t)stream>>>((const float*)x, npix, c8n, (uint32_t)(H * W), N, layout,
+                                                                                    (const uint32_t*)amax_bits, (__half*)out);
+        GT_CUDA_LAUNCH_CHECK("gt_f16x3_split_act");
+        return GT_OK;
+    }
     split_act_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const float*)x, s_n, s_c, s_h, s_w, N, C, H, W, Cp, layout, (const uint32_t*)amax_bits,
                                                                         (__half*)out);
     GT_CUDA_LAUNCH_CHECK("gt_f16x3_split_act");
@@ -190,9 +286,8 @@ extern "C" int gt_f16x3_pack_weight(const void* w, long long s_co, long long s_c
                                     int Cinp, const void* amax_bits, void* out, void* stream) {
     GT_REQUIRE(w && out && amax_bits, "gt_f16x3_pack_weight: null pointer");
     GT_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && Coutp >= Cout && Cinp >= Cin && Coutp % 64 == 0 && Cinp % 64 == 0, "gt_f16x3_pack_weight: bad shape");
-    const long long total = (long long)KH * KW * Coutp * Cinp;
-    pack_weight_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const float*)w, s_co, s_ci, s_r, s_s, Cout, Cin, KH, KW, Coutp, Cinp,
-                                                                          (const uint32_t*)amax_bits, (__half*)out);
+    pack_weight_pair_kernel<<<grid_for((long long)Coutp * Cinp), 256, 0, (cudaStream_t)stream>>>((const float*)w, s_co, s_ci, s_r, s_s, Cout, Cin, KH, KW, Coutp,
+                                                                                                 Cinp, (const uint32_t*)amax_bits, (__half*)out);
     GT_CUDA_LAUNCH_CHECK("gt_f16x3_pack_weight");
     return GT_OK;
 }
