@@ -44,7 +44,9 @@ def parse_args():
     ap.add_argument('--aug', default='ada', choices=['ada', 'noaug'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-rooflines', action='store_true', help='skip the per-kernel roofline microbenchmarks (scaling runs)')
     ap.add_argument('--no-overlap', action='store_true')
+    ap.add_argument('--graph-overlap', action='store_true', help='capture the bucketed gradient exchange inside each phase graph (opt-in, see Trainer.graph_overlap)')
     ap.add_argument('--two-pass-dmain', action='store_true', help='score generated and real images in two discriminator passes (the reference schedule) instead of one merged pass')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying per-phase CUDA graphs')
     ap.add_argument('--cpu-batch', type=int, default=4)
@@ -371,7 +373,8 @@ def run_ours(args):
     conv_igemm.call_log = {}
     gamma = 0.0002 * res ** 2 / global_batch if res != 256 or global_batch != 32 else 0.4096
     cfg = tl.claro_config(resolution=res, batch=global_batch, num_gpus=world, cbase=cbase, aug=args.aug, gamma=gamma)
-    trainer = tl.Trainer(cfg, rank=rank, device=device, overlap=not args.no_overlap, use_graphs=not args.no_graphs, merge_d_passes=not args.two_pass_dmain)
+    trainer = tl.Trainer(cfg, rank=rank, device=device, overlap=not args.no_overlap, use_graphs=not args.no_graphs, merge_d_passes=not args.two_pass_dmain,
+                         graph_overlap=args.graph_overlap)
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_img = (torch.rand([batch_gpu, 1, res, res], generator=g) * 255).pin_memory()
@@ -446,11 +449,29 @@ def run_ours(args):
         e2e = {'value': global_batch * args.steps / 1000.0 / (ms_e2e * 1e-3), 'unit': 'kimg/s',
                'h2d_bytes_per_step': int(host_img.numel() * 4 + host_c.numel() * 4) * world, 'd2h_bytes_per_step': 4 * world}
 
+    nccl_ms = None
     if world > 1:
         trainer.check_consistency()
+        # stand-alone cost of the per-phase exchange: one sum-all-reduce of each module's flat fp32 gradient (what the reference sends,
+        # S3/training/training_loop_mi_multimodal.py:340-351), CUDA events, max over ranks
+        nccl_ms = {}
+        for name, module in [('G', trainer.G), ('D', trainer.D)]:
+            buf = torch.zeros([sum(p.numel() for p in module.parameters())], device=device)
+            for _ in range(3):
+                torch.distributed.all_reduce(buf)
+            barrier()
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s3.record()
+            for _ in range(10):
+                torch.distributed.all_reduce(buf)
+            e3.record()
+            barrier()
+            t = max_over_ranks(s3.elapsed_time(e3) / 10)
+            nccl_ms[name] = {'bytes': buf.numel() * 4, 'ms': round(t, 4), 'bus_GBps': round(2 * (world - 1) / world * buf.numel() * 4 / (t * 1e-3) / 1e9, 1)}
+            del buf
 
     pk = peaks()
-    roof_all = hot_kernel_rooflines(device, pk) if rank == 0 else None
+    roof_all = hot_kernel_rooflines(device, pk) if (rank == 0 and not args.no_rooflines) else None
     roof = None
     if roof_all:
         dom, dom_ms = dominant_kernel(trainer, phase_counts, roof_all, batch_gpu)
@@ -472,7 +493,9 @@ def run_ours(args):
                                    f'lazy R1 (every 16) + path-length (every 4), ADA={args.aug}', 'global_batch': global_batch, 'batch_gpu': batch_gpu,
                        'parallelism': f'dp{world}', 'phase_counts_in_timed_region': phase_counts,
                        'l2_policy': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush in the step loop',
-                       'conv_routes': conv_stats, 'allow_igemm': conv_backend.allow_igemm, 'allow_library': conv_backend.allow_library, 'cuda_graphs': not args.no_graphs, 'dmain_one_pass': not args.two_pass_dmain, 'phase_ms': phase_ms},
+                       'conv_routes': conv_stats, 'allow_igemm': conv_backend.allow_igemm, 'allow_library': conv_backend.allow_library, 'cuda_graphs': not args.no_graphs, 'exchange': ('bucketed all-reduce on a side stream inside each phase graph, overlapped with backward' if trainer.graph_overlap
+                                                                       else 'one all-reduce of the flat gradient between two half-graphs') if world > 1 else 'none (1 GPU)',
+                       'nccl_allreduce_alone': nccl_ms, 'dmain_one_pass': not args.two_pass_dmain, 'phase_ms': phase_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base, 'roofline_all': roof_all,
         }
         if flops_per_img:
@@ -480,6 +503,13 @@ def run_ours(args):
             line['model_tensor_frac'] = line['model_tflops'] / world / pk['tflops_sustained']
         print(json.dumps(line), flush=True)
     if world > 1:
+        # drop the captured graphs before the communicator goes away, then leave without waiting on NCCL teardown
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        del trainer
+        import gc
+        gc.collect()
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

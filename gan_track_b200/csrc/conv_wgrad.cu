@@ -199,21 +199,34 @@ struct WgradOut {
     int f32, UCr, SCr;
     const uint32_t *amax_u, *amax_s;
 };
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int UC, int SC, int KW, const WgradOut o) {
-    const long long per = (long long)ntaps * UC * SC;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int UC, int SC, int KW, const WgradOut o) {
+    // one thread = one (u, s) channel pair, all taps: the workspace reads are coalesced along s for every tap and split, and the
+    // taps of a pair are adjacent in the weight layout, so the (fp16 or fp32) stores of a warp cover one contiguous run
+    const long long pairs = (long long)UC * SC;
+    const long long per = (long long)ntaps * pairs;
     const float inv = o.f32 ? (1.f / gt_scale_from_amax_bits(*o.amax_u)) * (1.f / gt_scale_from_amax_bits(*o.amax_s)) : 1.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x) {
         const int s = (int)(i % SC);
-        long long rest = i / SC;
-        const int u = (int)(rest % UC);
+        const int u = (int)(i / SC);
         if (u >= o.UCr || s >= o.SCr) continue;
-        float acc = 0.f;
-        for (int sp = 0; sp < splits; sp++) acc += ws[sp * per + i];
-        const int tap = (int)(rest / UC);
-        const int r = tap / KW, c = tap - r * KW;
-        const long long off = u * o.ds_u + s * o.ds_s + r * o.ds_r + c * o.ds_c;
-        if (o.f32) ((float*)o.dw)[off] = acc * inv;
-        else ((__half*)o.dw)[off] = __float2half_rn(acc);
+        float acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) acc[t] = 0.f;
+        for (int sp = 0; sp < splits; sp++) {                      // fixed split order: deterministic
+            const float* p = ws + sp * per + i;
+#pragma unroll
+            for (int t = 0; t < 9; t++)
+                if (t < ntaps) acc[t] += p[t * pairs];
+        }
+        const long long base = u * o.ds_u + s * o.ds_s;
+#pragma unroll
+        for (int t = 0; t < 9; t++)
+            if (t < ntaps) {
+                const int r = t / KW, c = t - r * KW;
+                const long long off = base + r * o.ds_r + c * o.ds_c;
+                if (o.f32) ((float*)o.dw)[off] = acc[t] * inv;
+                else ((__half*)o.dw)[off] = __float2half_rn(acc[t]);
+            }
     }
 }
 
@@ -315,8 +328,7 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
         const int splits = gt_launch_wgrad_halo(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, pad, workspace, workspace_floats,
                                                 (cudaStream_t)stream);
         if (splits <= 0) return GT_ERR_CUDA;
-        const long long per = (long long)ntaps * UC * SC;
-        long long g = (per + 255) / 256;
+        long long g = ((long long)UC * SC + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
         wgrad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, splits, ntaps, UC, SC, KW, wo);
         GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
@@ -373,9 +385,8 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
     cudaStream_t stm = (cudaStream_t)stream;
     int rc = (pl.BN == 128) ? launch_wgrad<128, 3>(tmU, tmS, p, pl.u_tiles, stm) : launch_wgrad<64, 4>(tmU, tmS, p, pl.u_tiles, stm);
     if (rc != GT_OK) return rc;
-    const long long per = (long long)ntaps * UC * SC;
     const int block = 256;
-    long long g = (per + block - 1) / block;
+    long long g = ((long long)UC * SC + block - 1) / block;
     if (g > 148 * 16) g = 148 * 16;
     wgrad_reduce_kernel<<<(int)g, block, 0, stm>>>(workspace, pl.splits, ntaps, UC, SC, KW, wo);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");

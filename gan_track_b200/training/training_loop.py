@@ -152,7 +152,8 @@ class GradBucketReducer:
                 torch.distributed.all_reduce(flat)
                 flat.div_(self.world_size)
                 torch.nan_to_num(flat, nan=0, posinf=1e5, neginf=-1e5, out=flat)
-            flat.record_stream(self.comm_stream)
+            if not torch.cuda.is_current_stream_capturing():
+                flat.record_stream(self.comm_stream)      # (inside a capture `_handles` keeps the bucket alive until finish() has joined the side stream)
         else:                               # CPU / gloo (tests): same bucketing, synchronous exchange
             torch.distributed.all_reduce(flat)
             flat.div_(self.world_size)
@@ -186,7 +187,7 @@ class GradBucketReducer:
 
 
 class Trainer:
-    def __init__(self, cfg, rank=0, device=None, overlap=True, ops_sanity=True, use_graphs=False, merge_d_passes=None):
+    def __init__(self, cfg, rank=0, device=None, overlap=True, ops_sanity=True, use_graphs=False, merge_d_passes=None, graph_overlap=False):
         self.cfg = cfg
         self.rank = rank
         self.num_gpus = cfg.num_gpus
@@ -200,6 +201,13 @@ class Trainer:
         grid_sample_gradfix.enabled = True
 
         self.use_graphs = bool(use_graphs) and self.device.type == 'cuda'
+        # Graph mode on several GPUs.  graph_overlap=True: the whole phase is ONE graph in which the bucketed gradient exchange runs on a
+        # side stream, forked from the backward pass by the parameters' post-accumulate hooks, so that NCCL overlaps the rest of backward.
+        # False (default): two graphs around one eager all-reduce of the flat gradient (the reference also exchanges once, after
+        # backward: training_loop_mi_multimodal.py:340-351).  Measured on 2 x B200 (profiles/r02_scaling_notes.md): the exchange is
+        # 0.22 ms of a 17 ms phase, the overlapped form is not faster (43.8 vs 42.5 ms/step: three extra passes over the gradient) and
+        # processes with captured NCCL work did not shut down cleanly, so it stays opt-in.
+        self.graph_overlap = bool(graph_overlap) and bool(overlap) and cfg.num_gpus > 1 and self.use_graphs
         if self.use_graphs and cfg.loss_kwargs.get('blur_fade_kimg', 0) != 0:
             # a captured phase freezes host-side scalars derived from cur_nimg (blur_sigma and the blur taps, loss.py) at their
             # capture-time value, whereas the reference fades them (S3/training/loss.py:70); the StyleGAN2 configs use 0
@@ -232,7 +240,7 @@ class Trainer:
         self.phases = []
         for name, module, opt_kwargs, reg_interval in [('G', self.G, cfg.G_opt_kwargs, cfg.G_reg_interval), ('D', self.D, cfg.D_opt_kwargs, cfg.D_reg_interval)]:
             params = list(module.parameters())
-            reducer = GradBucketReducer(params, self.num_gpus, overlap=overlap and not self.use_graphs)
+            reducer = GradBucketReducer(params, self.num_gpus, overlap=overlap)
             adam_extra = dict(capturable=True, foreach=True) if self.use_graphs else {}
             if reg_interval is None:
                 opt = torch.optim.Adam(params, **opt_kwargs, **adam_extra)
@@ -347,9 +355,15 @@ class Trainer:
     def _phase_half_a(self, phase, st):
         phase.opt.zero_grad(set_to_none=True)
         phase.module.requires_grad_(True)
+        if self.graph_overlap:
+            phase.reducer.begin(phase.grad_set)          # None on the first (eager) occurrence: the hooks only count
         self.loss.accumulate_gradients(phase=phase.name, real_img=st.real_img, real_c=st.real_c, gen_z=st.gen_z, gen_c=st.gen_c,
                                        gain=phase.interval, cur_nimg=self.cur_nimg)
         phase.module.requires_grad_(False)
+        if self.graph_overlap:
+            if phase.grad_set is None and phase.reducer.fire_counts:
+                phase.grad_set = dict(phase.reducer.fire_counts)
+            phase.reducer.finish()                       # joins the side stream; .grad now holds sum / num_gpus, scrubbed
         st.with_grad = [p for p in phase.module.parameters() if p.grad is not None]
         st.active_idx = [i for i, p in enumerate(phase.module.parameters()) if p.grad is not None]
         st.flat = torch.cat([p.grad.flatten() for p in st.with_grad])
@@ -357,10 +371,10 @@ class Trainer:
     def _phase_half_b(self, phase, st):
         if phase.get('flat_opt') is not None:
             # /num_gpus, nan_to_num and Adam in one kernel over the flat gradient (parameters without a gradient are skipped)
-            phase.flat_opt.step(phase.name, st.active_idx, st.flat, grad_scale=1.0 / self.num_gpus)
+            phase.flat_opt.step(phase.name, st.active_idx, st.flat, grad_scale=1.0 if self.graph_overlap else 1.0 / self.num_gpus)
             return
         flat = st.flat
-        if self.num_gpus > 1:
+        if self.num_gpus > 1 and not self.graph_overlap:
             flat = flat / self.num_gpus
         flat = misc.nan_to_num(flat, nan=0, posinf=1e5, neginf=-1e5)
         for p, g in zip(st.with_grad, flat.split([p.numel() for p in st.with_grad])):
@@ -380,7 +394,7 @@ class Trainer:
         st.gen_c.copy_(g_c)
         if phase.graphs is None and phase.eager_runs < 1:         # warm-up occurrence: eager
             self._phase_half_a(phase, st)
-            if self.num_gpus > 1:
+            if self.num_gpus > 1 and not self.graph_overlap:
                 torch.distributed.all_reduce(st.flat)
             self._phase_half_b(phase, st)
             phase.eager_runs += 1
@@ -391,7 +405,7 @@ class Trainer:
             log0 = dict(conv_igemm.call_log) if conv_igemm.call_log is not None else None
             torch.cuda.synchronize()
             ga = torch.cuda.CUDAGraph()
-            if self.num_gpus == 1:
+            if self.num_gpus == 1 or self.graph_overlap:
                 with torch.cuda.graph(ga):
                     self._phase_half_a(phase, st)
                     self._phase_half_b(phase, st)
