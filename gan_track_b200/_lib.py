@@ -56,6 +56,7 @@ _PROTOTYPES = {
     'gt_torgb1_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _ll, _i, _vp]),
     'gt_torgb1_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _i, _vp]),
     'gt_conv_igemm_config': (_i, [_i]),
+    'gt_conv_rows_config': (_i, [_i]),
     'gt_conv_wgrad_config': (_i, [_i]),
     'gt_conv_pack_weight_f16': (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp, _vp]),
     'gt_conv2d_igemm_f16': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -89,3 +89,8 @@ __device__ __forceinline__ void conv_store32(const ConvParams& p, long long elem
 int gt_launch_conv_halo(const void* x, long long xs_n, long long xs_h, long long xs_w, int H, int W, const void* wpacked, int ntaps_total, ConvParams& p,
                         cudaStream_t stream);
 bool gt_conv_halo_applicable(const ConvParams& p, int maxOH, int maxOW);
+
+// conv_rows.cu: row-streaming kernel for the 64 -> 64 channel 3x3 stride-1 layers
+bool gt_conv_rows_applicable(const ConvParams& p, int H, int W);
+int gt_launch_conv_rows(const void* x, long long xs_n, long long xs_h, long long xs_w, int H, int W, const void* wpacked, int ntaps_total, const ConvParams& p,
+                        cudaStream_t stream);

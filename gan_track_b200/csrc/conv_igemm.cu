@@ -369,6 +369,8 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     p.tiles_h = (maxOH + bh - 1) / bh;
     p.tiles_n = (N + bn - 1) / bn;
 
+    if (g_conv_variant != 1 && gt_conv_rows_applicable(p, H, W))
+        return gt_launch_conv_rows(x, xs_n, xs_h, xs_w, H, W, wpacked, KH * KW, p, (cudaStream_t)stream);
     if (g_conv_variant != 1 && p.in_stride == 1 && gt_conv_halo_applicable(p, maxOH, maxOW))
         return gt_launch_conv_halo(x, xs_n, xs_h, xs_w, H, W, wpacked, KH * KW, p, (cudaStream_t)stream);
 

@@ -286,6 +286,7 @@ int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParam
 static int pair_mt(int Cout) { return Cout % 256 == 0 ? 1 : (Cout % 128 == 0 ? 2 : 4); }
 
 bool gt_conv_halo2_applicable(const ConvParams& p, int maxOH, int maxOW) {
+    if (p.nphases == 1 && p.ph[0].ntaps == 1) return false;      // 1x1: nothing to share between taps, the single-CTA kernel is faster (34 vs 38 us)
     return p.in_stride == 1 && conv_mode(p) == CONV_F16 && maxOH >= SUB_H && maxOW >= 2 * SUB_W * pair_mt(p.Cout);
 }
 

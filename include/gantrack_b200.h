@@ -89,6 +89,9 @@ int gt_upfirdn2d(const void* x, const float* f, void* y, int dtype, int N, int C
 /* Kernel selection for gt_conv2d_igemm_f16: 0 = automatic (halo-staged persistent kernel where it applies, per-tap kernel
  * otherwise), 1 = per-tap kernel only.  A negative value only queries.  Returns the previous setting. */
 int gt_conv_igemm_config(int variant);
+/* Row-streaming kernel for the 64 -> 64 channel 3x3 stride-1 layers (csrc/conv_rows.cu): 1 = used where it applies (default), 0 = off.
+ * Returns the previous value. */
+int gt_conv_rows_config(int enabled);
 int gt_conv_pack_weight_f16(const void* w, long long s_co, long long s_ci, long long s_r, long long s_s, int Cout, int Cin,
                             int KH, int KW, void* wpacked, void* stream);
 int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y,

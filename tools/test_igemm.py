@@ -49,6 +49,11 @@ CASES = [
     ('3x3 T s1 p1 64->128 40x40 n6', 6, 64, 128, 40, 40, 3, 1, 1, True),
     ('3x3 p0 64->64 66x66 n4', 4, 64, 64, 66, 66, 3, 1, 0, False),
     ('3x3 p1 256->256 32x32 n8', 8, 256, 256, 32, 32, 3, 1, 1, False),
+    # row-streaming kernel (csrc/conv_rows.cu): 64 -> 64, width >= 128; ragged widths / heights, transposed (= data gradient) form
+    ('3x3 p1 64->64 256x256 n2', 2, 64, 64, 256, 256, 3, 1, 1, False),
+    ('3x3 T s1 p1 64->64 130x200 n3', 3, 64, 64, 130, 200, 3, 1, 1, True),
+    ('3x3 p1 64->64 9x300 n2', 2, 64, 64, 9, 300, 3, 1, 1, False),
+    ('3x3 p1 64->64 257x129 n1', 1, 64, 64, 257, 129, 3, 1, 1, False),
 ]
 
 
