@@ -200,33 +200,28 @@ struct WgradOut {
     const uint32_t *amax_u, *amax_s;
 };
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int UC, int SC, int KW, const WgradOut o) {
-    // one thread = one (u, s) channel pair, all taps: the workspace reads are coalesced along s for every tap and split, and the
-    // taps of a pair are adjacent in the weight layout, so the (fp16 or fp32) stores of a warp cover one contiguous run
-    const long long pairs = (long long)UC * SC;
-    const long long per = (long long)ntaps * pairs;
+    // one thread = one (tap, u, s) element: reads coalesced along s for every split (four splits in flight), 32-bit index math.
+    // ~20 MB of partial sums whatever the layer (many splits x few channels ... few splits x many channels), so the thread count must
+    // not depend on the channel count alone.
+    const uint32_t pairs = (uint32_t)UC * (uint32_t)SC;
+    const uint32_t per = (uint32_t)ntaps * pairs;
     const float inv = o.f32 ? (1.f / gt_scale_from_amax_bits(*o.amax_u)) * (1.f / gt_scale_from_amax_bits(*o.amax_s)) : 1.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x) {
-        const int s = (int)(i % SC);
-        const int u = (int)(i / SC);
-        if (u >= o.UCr || s >= o.SCr) continue;
-        float acc[9];
-#pragma unroll
-        for (int t = 0; t < 9; t++) acc[t] = 0.f;
-        for (int sp = 0; sp < splits; sp++) {                      // fixed split order: deterministic
-            const float* p = ws + sp * per + i;
-#pragma unroll
-            for (int t = 0; t < 9; t++)
-                if (t < ntaps) acc[t] += p[t * pairs];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        const uint32_t tap = i / pairs, pr = i - tap * pairs;
+        const uint32_t u = pr / (uint32_t)SC, s = pr - u * (uint32_t)SC;
+        if ((int)u >= o.UCr || (int)s >= o.SCr) continue;
+        const float* p = ws + i;
+        float acc = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4) {                       // fixed order: ((((acc + p0) + p1) + p2) + p3) -- deterministic
+            const float a0 = p[(size_t)sp * per], a1 = p[(size_t)(sp + 1) * per], a2 = p[(size_t)(sp + 2) * per], a3 = p[(size_t)(sp + 3) * per];
+            acc = (((acc + a0) + a1) + a2) + a3;
         }
-        const long long base = u * o.ds_u + s * o.ds_s;
-#pragma unroll
-        for (int t = 0; t < 9; t++)
-            if (t < ntaps) {
-                const int r = t / KW, c = t - r * KW;
-                const long long off = base + r * o.ds_r + c * o.ds_c;
-                if (o.f32) ((float*)o.dw)[off] = acc[t] * inv;
-                else ((__half*)o.dw)[off] = __float2half_rn(acc[t]);
-            }
+        for (; sp < splits; sp++) acc += p[(size_t)sp * per];
+        const int r = (int)tap / KW, c = (int)tap - r * KW;
+        const long long off = (long long)u * o.ds_u + (long long)s * o.ds_s + r * o.ds_r + c * o.ds_c;
+        if (o.f32) ((float*)o.dw)[off] = acc * inv;
+        else ((__half*)o.dw)[off] = __float2half_rn(acc);
     }
 }
 
@@ -328,7 +323,7 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
         const int splits = gt_launch_wgrad_halo(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, pad, workspace, workspace_floats,
                                                 (cudaStream_t)stream);
         if (splits <= 0) return GT_ERR_CUDA;
-        long long g = ((long long)UC * SC + 255) / 256;
+        long long g = ((long long)ntaps * UC * SC + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
         wgrad_reduce_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, splits, ntaps, UC, SC, KW, wo);
         GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
@@ -386,7 +381,7 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
     int rc = (pl.BN == 128) ? launch_wgrad<128, 3>(tmU, tmS, p, pl.u_tiles, stm) : launch_wgrad<64, 4>(tmU, tmS, p, pl.u_tiles, stm);
     if (rc != GT_OK) return rc;
     const int block = 256;
-    long long g = ((long long)UC * SC + block - 1) / block;
+    long long g = ((long long)ntaps * UC * SC + block - 1) / block;
     if (g > 148 * 16) g = 148 * 16;
     wgrad_reduce_kernel<<<(int)g, block, 0, stm>>>(workspace, pl.splits, ntaps, UC, SC, KW, wo);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
