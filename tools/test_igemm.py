@@ -164,7 +164,10 @@ if args.time and fails == 0:
         if args.wgrad:
             dy = torch.randn([N, co, OH, OW], device=dev).to(torch.float16).contiguous(memory_format=torch.channels_last)
             t_w = bench(lambda: conv_igemm.igemm_wgrad(dy, x, tuple(wshape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1))
+            _lib.load().gt_conv_wgrad_config(1)
+            t_w1 = bench(lambda: conv_igemm.igemm_wgrad(dy, x, tuple(wshape), transpose=tr, output_padding=(0, 0), stride=(s, s), padding=(p, p), groups=1))
+            _lib.load().gt_conv_wgrad_config(0)
             t_wl = bench(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [s, s], [p, p], [1, 1], tr, [0, 0], 1, [False, True, False]))
-            line += f' || wgrad ours {t_w * 1e3:7.1f} us {flops / t_w / 1e9:6.0f} TF/s | cudnn {t_wl * 1e3:7.1f} us {flops / t_wl / 1e9:6.0f} TF/s'
+            line += f' || wgrad ours {t_w * 1e3:7.1f} us {flops / t_w / 1e9:6.0f} TF/s (per-tap-row {t_w1 * 1e3:6.1f}) | cudnn {t_wl * 1e3:7.1f} us {flops / t_wl / 1e9:6.0f} TF/s'
         print(line, flush=True)
 sys.exit(1 if fails else 0)
