@@ -26,6 +26,7 @@ _PROTOTYPES = {
     'gt_bias_act_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _i, _i, _ll, _vp]),
     'gt_upfirdn2d': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _ll, _ll, _i, _i, _ll, _ll, _ll, _ll,
                           _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    'gt_aug_params': (_i, [_c.POINTER(_c.c_void_p), _vp, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _i, _i, _i, _i, _vp, _vp, _vp]),
     'gt_aug_warp_workspace': (_ll, [_i, _i, _i, _i]),
     'gt_aug_warp_fwd': (_i, [_vp, _vp, _vp, _c.POINTER(_c.c_float), _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     'gt_aug_warp_bwd': (_i, [_vp, _vp, _vp, _c.POINTER(_c.c_float), _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp]),

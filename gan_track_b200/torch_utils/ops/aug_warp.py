@@ -84,3 +84,23 @@ def warp(x, theta, margins, taps, out_hw):
     them); margins: int32[4] device tensor (mx0, my0, mx1, my1), each in [0, W-1] / [0, H-1]; taps: tuple of floats
     (the normalised 1-D low-pass, even length <= 12)."""
     return _Warp.apply(x, theta, margins, tuple(float(t) for t in taps), (int(out_hw[0]), int(out_hw[1])))
+
+
+def params(draws, p, multipliers, ranges, B, H, W, hz_pad):
+    """All the geometric parameter algebra of the ADA pipe in one launch (csrc/augment_params.cu).  `draws`: 16 entries, (value
+    draw, gate draw) per transform in the pipe's order xflip, rotate90, xint, scale, rotate (pre), aniso, rotate (post), xfrac; None
+    for a disabled transform.  Returns (theta [B,2,3] fp32, margins int32 [4])."""
+    lib = _lib.load()
+    dev = p.device
+    assert len(draws) == 16
+    ptrs = (ctypes.c_void_p * 16)(*[(_lib.ptr(t.contiguous()) if t is not None else None) for t in draws])
+    keep = [t for t in draws if t is not None]        # (contiguous() of a fresh rand / randn is the tensor itself)
+    mult = (ctypes.c_float * 7)(*[float(m) for m in multipliers])
+    rng = (ctypes.c_float * 5)(*[float(r) for r in ranges])
+    theta = torch.empty([B, 2, 3], dtype=torch.float32, device=dev)
+    margins = torch.empty([4], dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gt_aug_params(ptrs, _lib.ptr(p), mult, rng, B, H, W, hz_pad, _lib.ptr(theta), _lib.ptr(margins), _lib.stream_of(theta)), 'gt_aug_params')
+    _lib.count_launch()
+    del keep
+    return theta, margins

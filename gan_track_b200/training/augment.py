@@ -108,6 +108,7 @@ class AugmentPipe(torch.nn.Module):
         self.register_buffer('Hz_geom', upfirdn2d.setup_filter(wavelets['sym6']))
         self._hz_geom_taps = tuple(float(v) for v in self.Hz_geom.tolist())     # host copy for the fused warp kernel
         self.fused_warp = True      # False: the reference's op-by-op sequence with the host read of the margins
+        self.fused_params = True    # the ~110 tiny ops between the random draws and the warp as one launch (csrc/augment_params.cu)
 
         # Band-pass bank for the image-space filter: H(z) = sym2 low-pass, dyadic cascade of 4 bands.
         lo = np.asarray(wavelets['sym2'])
@@ -137,50 +138,56 @@ class AugmentPipe(torch.nn.Module):
         # ---------------- geometric parameters -> G_inv ----------------
         I_3 = torch.eye(3, device=dev)
         G_inv = I_3
-        if self.xflip > 0:
+        geom_on = max(self.xflip, self.rotate90, self.xint, self.scale, self.rotate, self.aniso, self.xfrac) > 0
+        if geom_on and dbg is None and self.fused_params and self.fused_warp and images.is_cuda and images.dtype == torch.float32 and B <= 1024:
+            images = self._warp_fused_params(images)
+            geom_on = False
+        if not geom_on:
+            pass
+        elif self.xflip > 0:
             i = torch.floor(torch.rand([B], device=dev) * 2)
             i = self._gate([B], self.xflip * self.p, i, torch.zeros_like(i), dev)
             if dbg is not None:
                 i = torch.full_like(i, torch.floor(dbg * 2))
             G_inv = G_inv @ scale2d_inv(1 - 2 * i, 1)
-        if self.rotate90 > 0:
+        if geom_on and self.rotate90 > 0:
             i = torch.floor(torch.rand([B], device=dev) * 4)
             i = self._gate([B], self.rotate90 * self.p, i, torch.zeros_like(i), dev)
             if dbg is not None:
                 i = torch.full_like(i, torch.floor(dbg * 4))
             G_inv = G_inv @ rotate2d_inv(-np.pi / 2 * i)
-        if self.xint > 0:
+        if geom_on and self.xint > 0:
             t = (torch.rand([B, 2], device=dev) * 2 - 1) * self.xint_max
             t = self._gate([B, 1], self.xint * self.p, t, torch.zeros_like(t), dev)
             if dbg is not None:
                 t = torch.full_like(t, (dbg * 2 - 1) * self.xint_max)
             G_inv = G_inv @ translate2d_inv(torch.round(t[:, 0] * W), torch.round(t[:, 1] * H))
-        if self.scale > 0:
+        if geom_on and self.scale > 0:
             s = torch.exp2(torch.randn([B], device=dev) * self.scale_std)
             s = self._gate([B], self.scale * self.p, s, torch.ones_like(s), dev)
             if dbg is not None:
                 s = torch.full_like(s, torch.exp2(torch.erfinv(dbg * 2 - 1) * self.scale_std))
             G_inv = G_inv @ scale2d_inv(s, s)
-        p_rot = 1 - torch.sqrt((1 - self.rotate * self.p).clamp(0, 1))      # P(pre or post) = rotate * p
-        if self.rotate > 0:
+        p_rot = 1 - torch.sqrt((1 - self.rotate * self.p).clamp(0, 1)) if geom_on else None      # P(pre or post) = rotate * p
+        if geom_on and self.rotate > 0:
             th = (torch.rand([B], device=dev) * 2 - 1) * np.pi * self.rotate_max
             th = self._gate([B], p_rot, th, torch.zeros_like(th), dev)
             if dbg is not None:
                 th = torch.full_like(th, (dbg * 2 - 1) * np.pi * self.rotate_max)
             G_inv = G_inv @ rotate2d_inv(-th)
-        if self.aniso > 0:
+        if geom_on and self.aniso > 0:
             s = torch.exp2(torch.randn([B], device=dev) * self.aniso_std)
             s = self._gate([B], self.aniso * self.p, s, torch.ones_like(s), dev)
             if dbg is not None:
                 s = torch.full_like(s, torch.exp2(torch.erfinv(dbg * 2 - 1) * self.aniso_std))
             G_inv = G_inv @ scale2d_inv(s, 1 / s)
-        if self.rotate > 0:
+        if geom_on and self.rotate > 0:
             th = (torch.rand([B], device=dev) * 2 - 1) * np.pi * self.rotate_max
             th = self._gate([B], p_rot, th, torch.zeros_like(th), dev)
             if dbg is not None:
                 th = torch.zeros_like(th)
             G_inv = G_inv @ rotate2d_inv(-th)
-        if self.xfrac > 0:
+        if geom_on and self.xfrac > 0:
             t = torch.randn([B, 2], device=dev) * self.xfrac_std
             t = self._gate([B, 1], self.xfrac * self.p, t, torch.zeros_like(t), dev)
             if dbg is not None:
@@ -280,6 +287,35 @@ class AugmentPipe(torch.nn.Module):
             keep_y = (((cy + 0.5) / H - center[:, 1]).abs() >= size[:, 1] / 2)
             images = images * torch.logical_or(keep_x, keep_y).to(torch.float32)
         return images
+
+    def _warp_fused_params(self, images):
+        """Geometric augmentation with the parameter algebra in one kernel: the draws below are the reference's draws, in its order
+        and shapes (S3/training/augment_mi.py:213-276), so a fixed seed gives the reference's transform parameters."""
+        B, C, H, W = images.shape
+        dev = images.device
+        draws = []
+
+        def draw(on, value_shape, gate_shape, normal):
+            if not on:
+                draws.extend([None, None])
+                return
+            v = torch.randn(value_shape, device=dev) if normal else torch.rand(value_shape, device=dev)
+            g = torch.rand(gate_shape, device=dev)
+            draws.extend([v, g])
+        draw(self.xflip > 0, [B], [B], False)
+        draw(self.rotate90 > 0, [B], [B], False)
+        draw(self.xint > 0, [B, 2], [B, 1], False)
+        draw(self.scale > 0, [B], [B], True)
+        draw(self.rotate > 0, [B], [B], False)
+        draw(self.aniso > 0, [B], [B], True)
+        draw(self.rotate > 0, [B], [B], False)
+        draw(self.xfrac > 0, [B, 2], [B, 1], True)
+        Hz_pad = self.Hz_geom.shape[0] // 4
+        theta, margins = aug_warp.params(draws, self.p, (self.xflip, self.rotate90, self.xint, self.scale, self.rotate, self.aniso, self.xfrac),
+                                         (self.xint_max, self.scale_std, self.rotate_max, self.aniso_std, self.xfrac_std), B, H, W, Hz_pad)
+        out_hw = [(H + Hz_pad * 2) * 2, (W + Hz_pad * 2) * 2]
+        images = aug_warp.warp(images, theta, margins, self._hz_geom_taps, out_hw)
+        return upfirdn2d.downsample2d(x=images, f=self.Hz_geom, down=2, padding=-Hz_pad * 2, flip_filter=True)
 
     def _warp(self, images, G_inv):
         """Apply the inverse warp with 2x supersampling (reference :286-321)."""

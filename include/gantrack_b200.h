@@ -246,6 +246,13 @@ int gt_torgb1_bwd(const void* dy, const void* x, const float* s, const void* w, 
  * the call runs as two passes -- separable upsampling of the reflect-padded image into the workspace, then the 4-tap
  * bilinear resampling; with workspace == NULL as one 49-tap gather kernel.  gt_aug_warp_bwd is the adjoint (gx is
  * zeroed, then accumulated with atomicAdd; the workspace holds the gradient of the upsampled image). */
+/* The geometric parameter algebra of the pipe between its random draws and the warp (S3/training/augment_mi.py:213-312: gates, 3x3
+ * matrix chain, corner margins, normalisation to sampling coordinates) in one launch.  ptrs: 16 device pointers = (value draw, gate
+ * draw) per transform in the order xflip, rotate90, xint, scale, pre-rotation, aniso, post-rotation, xfrac, NULL value = disabled;
+ * p: device scalar (ADA strength); mult: 7 probability multipliers (rotate once); ranges: xint_max, scale_std, rotate_max, aniso_std,
+ * xfrac_std.  Outputs: theta [B,2,3] fp32 and margins int32[4] as gt_aug_warp_fwd takes them.  B <= 1024. */
+int gt_aug_params(const void* const* ptrs, const float* p, const float* mult, const float* ranges, int B, int H, int W, int hz_pad,
+                  void* theta, void* margins, void* stream);
 long long gt_aug_warp_workspace(int B, int C, int H, int W);
 int gt_aug_warp_fwd(const float* x, const float* theta, const int* margins, const float* taps_host, int ntaps, float* y, int B,
                     int C, int H, int W, int OH, int OW, float* workspace, long long workspace_floats, void* stream);

