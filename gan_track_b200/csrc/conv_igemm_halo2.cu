@@ -100,7 +100,7 @@ __device__ __forceinline__ Item2 decode_item2(const ConvParams& p, int item, int
     return it;
 }
 
-template <int BN, int MT, int SB>
+template <int BN, int MT, int SB, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     conv_igemm_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p, const int total_items) {
     typedef Halo2Smem<BN, MT, SB> L;
@@ -243,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c * 32), r);
                     tmem_ld_wait();
-                    if (valid) conv_store32<CONV_F16>(p, yoff + c * 32, it.nt * BN + c * 32, r);
+                    if (valid) conv_store32<MODE>(p, yoff + c * 32, it.nt * BN + c * 32, r);
                 }
             }
             tc_fence_before();
@@ -261,12 +261,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     }
 }
 
-template <int BN, int MT, int SB>
-int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
+template <int BN, int MT, int SB, int MODE>
+int launch_halo2_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
     typedef Halo2Smem<BN, MT, SB> L;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_halo2_kernel<BN, MT, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_halo2_kernel<BN, MT, SB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
         if (e != cudaSuccess) {
             gt_set_error("gt_conv2d_igemm (halo, CTA pair): cannot reserve %u bytes of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
             return GT_ERR_CUDA;
@@ -275,19 +275,25 @@ int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParam
     }
     int clusters = gt_num_sms() / 2;
     if (clusters > total_items) clusters = total_items;
-    conv_igemm_halo2_kernel<BN, MT, SB><<<2 * clusters, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
+    conv_igemm_halo2_kernel<BN, MT, SB, MODE><<<2 * clusters, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm (halo, CTA pair)");
     return GT_OK;
 }
 
+template <int BN, int MT, int SB>
+int launch_halo2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int total_items, cudaStream_t stream) {
+    if (conv_mode(p) == CONV_F16_EP) return launch_halo2_m<BN, MT, SB, CONV_F16_EP>(tmA, tmB, p, total_items, stream);
+    return launch_halo2_m<BN, MT, SB, CONV_F16>(tmA, tmB, p, total_items, stream);
+}
+
 }  // namespace
 
-// Plain fp16 mode only; the caller (gt_launch_conv_halo) has filled dy_min / dx_min and checked the tap extent.
+// fp16 output modes (plain and fused bias_act epilogue); the caller (gt_launch_conv_halo) has filled dy_min / dx_min and checked the tap extent.
 static int pair_mt(int Cout) { return Cout % 256 == 0 ? 1 : (Cout % 128 == 0 ? 2 : 4); }
 
 bool gt_conv_halo2_applicable(const ConvParams& p, int maxOH, int maxOW) {
     if (p.nphases == 1 && p.ph[0].ntaps == 1) return false;      // 1x1: nothing to share between taps, the single-CTA kernel is faster (34 vs 38 us)
-    return p.in_stride == 1 && conv_mode(p) == CONV_F16 && maxOH >= SUB_H && maxOW >= 2 * SUB_W * pair_mt(p.Cout);
+    return p.in_stride == 1 && conv_mode(p) != CONV_F32OUT && maxOH >= SUB_H && maxOW >= 2 * SUB_W * pair_mt(p.Cout);
 }
 
 int gt_launch_conv_halo2(const void* x, long long xs_n, long long xs_h, long long xs_w, int H, int W, const void* wpacked, int ntaps_total, ConvParams& p,
