@@ -27,6 +27,9 @@ x512 = t([32, 512, 32, 32]); w512 = t([512, 512, 3, 3]) * 0.015           # G b3
 x256 = t([32, 256, 64, 64]); w256 = t([256, 256, 3, 3]) * 0.02            # G b64 conv1 / D b64 conv0
 x64 = t([32, 64, 256, 256]); w64 = t([64, 64, 3, 3]) * 0.04               # G b256 conv1 / D b256 conv0
 x128 = t([32, 128, 128, 128]); wT = t([128, 64, 3, 3]) * 0.03             # G b256 conv0 (transposed stride 2)
+w128 = t([128, 128, 3, 3]) * 0.03                                           # G b128 conv1 / D b128 conv0
+xd = t([32, 64, 257, 257]); wd = t([128, 64, 3, 3]) * 0.04                  # D b256 conv1 (blurred, stride 2)
+x32f = torch.randn([32, 512, 16, 16], device=dev); w32f = torch.randn([512, 512, 3, 3], device=dev) * 0.015   # G b16 conv1 (fp32)
 xb = t([32, 64, 257, 257])
 xu = t([32, 64, 128, 128])                                                # backward of the D skip downsample
 f = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
@@ -45,8 +48,14 @@ for _ in range(a.reps + 1):
     conv_igemm.igemm_forward(x256, w256, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     conv_igemm.igemm_forward(x64, w64, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     conv_igemm.igemm_forward(x128, wT, transpose=True, stride=(2, 2), padding=(0, 0), **cfg)
+    conv_igemm.igemm_forward(x128, w128, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    conv_igemm.igemm_forward(xd, wd, transpose=False, stride=(2, 2), padding=(0, 0), **cfg)
+    conv_igemm.igemm_wgrad(x512, x512, (512, 512, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     conv_igemm.igemm_wgrad(x256, x256, (256, 256, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    conv_igemm.igemm_wgrad(x128, x128, (128, 128, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     conv_igemm.igemm_wgrad(x64, x64, (64, 64, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
+    conv_igemm.igemm_forward(x32f, w32f, transpose=False, stride=(1, 1), padding=(1, 1), **cfg)     # fp32 block on the fp16 x 3 route
+    conv_igemm.igemm_wgrad(x32f, x32f, (512, 512, 3, 3), transpose=False, stride=(1, 1), padding=(1, 1), **cfg)
     upfirdn2d.upfirdn2d(xb, f, padding=[1, 1, 1, 1], gain=4)
     upfirdn2d.upfirdn2d(x64, f, down=2, padding=[1, 1, 1, 1])
     upfirdn2d.upfirdn2d(xu, f, up=2, padding=[2, 1, 2, 1], gain=4)
