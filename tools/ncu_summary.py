@@ -8,7 +8,9 @@ import sys
 
 rep = sys.argv[1]
 header = sys.argv[2] if len(sys.argv) > 2 else ''
-out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+# a .csv argument is the already exported raw page (`ncu -i x.ncu-rep --page raw --csv` run on the GPU box: reports with --import-source
+# exceed the 64 MiB that travel back)
+out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
