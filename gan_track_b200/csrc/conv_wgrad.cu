@@ -26,16 +26,19 @@ using namespace sm100;
 
 // conv_wgrad_halo.cu: halo-staged, tap-paired kernel for the stride-1 3x3 layers
 bool gt_wgrad_halo_applicable(int N, int UH, int UW, int UC, int SC, int SH, int SW, int KH, int KW, int stride, int pad);
-long long gt_wgrad_halo_workspace(int N, int UH, int UW, int UC, int SC);
+long long gt_wgrad_halo_workspace(int N, int UH, int UW, int UC, int SC, int stride);
 int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n, long long ss_h,
-                         long long ss_w, int SH, int SW, int SC, int N, int pad, float* workspace, long long workspace_floats, cudaStream_t stream);
-static int g_wgrad_variant = 0;   // 0 = auto (halo kernel where it applies), 1 = per-tap-row kernel only
+                         long long ss_w, int SH, int SW, int SC, int N, int stride, int pad, float* workspace, long long workspace_floats,
+                         cudaStream_t stream);
+void gt_wgrad_halo_enable_s2(int on);
+static int g_wgrad_variant = 0;   // 0 = auto (halo kernel where it applies), 1 = per-tap-row kernel only, 2 = halo kernel for stride 1 only
 // > 0: at most this many pixels per split-K slice.  Set (per calling thread) around the fp16x3 entry points: the tensor core's truncating
 // accumulation must stay below ~100 main-term updates per accumulator for fp32 accuracy (csrc/conv_f16x3.cu).
 thread_local int t_wgrad_px_limit = 0;
 extern "C" int gt_conv_wgrad_config(int variant) {
     const int old = g_wgrad_variant;
     g_wgrad_variant = variant;
+    gt_wgrad_halo_enable_s2(variant != 2);
     return old;
 }
 
@@ -298,9 +301,11 @@ static long long wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, 
     if (N <= 0 || UH <= 0 || UW <= 0 || UC <= 0 || SC <= 0 || KH <= 0 || KW <= 0) return 0;
     WgradPlan pl = make_plan(N, UH, UW, UC, SC, KH * KW);
     long long need = (long long)pl.splits * KH * KW * UC * SC;
-    if (KH == 3 && KW == 3 && UC % 64 == 0 && SC % 64 == 0) {           // the halo kernel may take the call: cover its plan too
-        const long long h = gt_wgrad_halo_workspace(N, UH, UW, UC, SC);
-        if (h > need) need = h;
+    if (KH == 3 && KW == 3 && UC % 64 == 0 && SC % 64 == 0) {           // the halo kernel may take the call: cover its plans too
+        for (int stride = 1; stride <= 2; stride++) {
+            const long long h = gt_wgrad_halo_workspace(N, UH, UW, UC, SC, stride);
+            if (h > need) need = h;
+        }
     }
     return need;
 }
@@ -319,8 +324,8 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
     GT_REQUIRE(us_w % 8 == 0 && us_h % 8 == 0 && us_n % 8 == 0 && ss_w % 8 == 0 && ss_h % 8 == 0 && ss_n % 8 == 0,
                "gt_conv2d_wgrad_f16: strides must be multiples of 8 elements");
     const int ntaps = KH * KW;
-    if (g_wgrad_variant == 0 && gt_wgrad_halo_applicable(N, UH, UW, UC, SC, SH, SW, KH, KW, stride, pad)) {
-        const int splits = gt_launch_wgrad_halo(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, pad, workspace, workspace_floats,
+    if (g_wgrad_variant != 1 && gt_wgrad_halo_applicable(N, UH, UW, UC, SC, SH, SW, KH, KW, stride, pad)) {
+        const int splits = gt_launch_wgrad_halo(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, stride, pad, workspace, workspace_floats,
                                                 (cudaStream_t)stream);
         if (splits <= 0) return GT_ERR_CUDA;
         long long g = ((long long)ntaps * UC * SC + 255) / 256;

@@ -22,6 +22,14 @@
 //   * A CTA owns one (64 S-channel, 64 U-channel) tile and a slice of the pixel tiles (split-K); fp32 partials go to the
 //     workspace [split][tap][u][s] and wgrad_reduce sums them in split order (deterministic, conv_wgrad.cu).
 // Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; STAGES x {U 16 KB, S 23 KB}.
+//
+// STRIDE = 2 (weight gradient of the discriminator's stride-2 down-convolutions and of the generator's transposed stride-2
+// up-convolutions, pad 0):  S is read at (2 i + r, 2 j + s).  The footprint is staged as its four PARITY PLANES
+// P[pr][ps][y][x] = S[2 (i0 + y) + pr][2 (j0 + x) + ps] -- four TMA boxes of (8 + 1) x (8 + 1) pixels with element strides 2 -- so that
+// tap (r, s) is again a dense window: plane (r & 1, s & 1) shifted by (r >> 1, s >> 1).  The taps are paired in the order of their
+// byte offsets inside the stage (the descriptor's LBO is unsigned); everything else is the stride-1 kernel with an 8 x 8 pixel tile.
+// The per-tap-row kernel these cases used before fetched every S tile once per tap and was bound by L2 -> SM traffic
+// (137-189 us against 61-139 us for the library at the training shapes, profiles/r02n_evidence_call_stdout.txt).
 #include "gt_common.cuh"
 #include "gt_sm100.cuh"
 
@@ -32,15 +40,54 @@ extern thread_local int t_wgrad_px_limit;      // conv_wgrad.cu: > 0 = at most t
 namespace {
 
 constexpr int NTHREADS = 192;
-constexpr int TW = 8, TH = 16;                 // pixel tile (8-pixel rows = one MN-major 8-row group)
-constexpr int HW_ = TW + 2, HH_ = TH + 2;      // staged S footprint for 3x3
+constexpr int TW = 8;                          // pixel tile width (8-pixel rows = one MN-major 8-row group)
 constexpr int STAGES = 4;
-constexpr uint32_t U_BYTES = TW * TH * 128;                                   // 16 KB
-constexpr uint32_t S_BYTES = ((HW_ * HH_ * 128 + 1023) / 1024) * 1024;        // 23 KB (23040 used)
-constexpr uint32_t STAGE_BYTES = U_BYTES + S_BYTES;
-constexpr uint32_t SMEM_TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 8 + 1024;
 constexpr int NPAIRS = 5;
 constexpr uint32_t TMEM_COLS = 512;            // 5 x 64 accumulator columns, rounded up to a power of two
+
+// geometry of one pipeline stage: {U tile | staged S footprint}
+template <int STRIDE>
+struct Geo;
+template <>
+struct Geo<1> {
+    static constexpr int TH = 16;                                                  // pixel tile height
+    static constexpr int PW = TW + 2, PH = TH + 2;                                 // staged S footprint for 3x3
+    static constexpr int NPLANES = 1;
+    static constexpr uint32_t PLANE_BYTES = ((PW * PH * 128 + 1023) / 1024) * 1024;   // 23 KB (23040 used)
+    static constexpr uint32_t PLANE_TX = PW * PH * 128;
+    // tap t = r * 3 + s in pairing order, and its byte offset inside the staged footprint
+    __host__ __device__ static constexpr int tap_of(int i) { return i; }
+    __host__ __device__ static constexpr uint32_t off_of(int tap) { return (uint32_t)((tap / 3) * PW + (tap % 3)) * 128u; }
+};
+template <>
+struct Geo<2> {
+    static constexpr int TH = 8;
+    static constexpr int PW = TW + 1, PH = TH + 1;                                 // one parity plane: 9 x 9 pixels
+    static constexpr int NPLANES = 4;
+    static constexpr uint32_t PLANE_BYTES = ((PW * PH * 128 + 1023) / 1024) * 1024;   // 11 KB (10368 used)
+    static constexpr uint32_t PLANE_TX = PW * PH * 128;
+    __host__ __device__ static constexpr uint32_t off_of(int tap) {
+        return (uint32_t)((((tap / 3) & 1) * 2 + ((tap % 3) & 1))) * PLANE_BYTES + (uint32_t)(((tap / 3) >> 1) * PW + ((tap % 3) >> 1)) * 128u;
+    }
+    // taps sorted by off_of(): (0,0) (0,2) (2,0) (2,2) | (0,1) (2,1) | (1,0) (1,2) | (1,1)
+    __host__ __device__ static constexpr int tap_of(int i) {
+        return i == 0 ? 0 : i == 1 ? 2 : i == 2 ? 6 : i == 3 ? 8 : i == 4 ? 1 : i == 5 ? 7 : i == 6 ? 3 : i == 7 ? 5 : 4;
+    }
+};
+template <int STRIDE>
+struct StageLayout {
+    typedef Geo<STRIDE> G;
+    static constexpr uint32_t U_BYTES = TW * G::TH * 128;
+    static constexpr uint32_t S_BYTES = G::NPLANES * G::PLANE_BYTES;
+    static constexpr uint32_t STAGE_BYTES = U_BYTES + S_BYTES;
+    static constexpr uint32_t TX_BYTES = U_BYTES + G::NPLANES * G::PLANE_TX;
+    static constexpr uint32_t SMEM_TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 8 + 1024;
+};
+static_assert(Geo<2>::off_of(0) < Geo<2>::off_of(2) && Geo<2>::off_of(2) < Geo<2>::off_of(6) && Geo<2>::off_of(6) < Geo<2>::off_of(8) &&
+                  Geo<2>::off_of(8) < Geo<2>::off_of(1) && Geo<2>::off_of(1) < Geo<2>::off_of(7) && Geo<2>::off_of(7) < Geo<2>::off_of(3) &&
+                  Geo<2>::off_of(3) < Geo<2>::off_of(5) && Geo<2>::off_of(5) < Geo<2>::off_of(4),
+              "stride-2 taps must be paired in increasing offset order");
+static_assert(StageLayout<2>::SMEM_TOTAL <= 232448 && StageLayout<1>::SMEM_TOTAL <= 232448, "stage ring exceeds the shared memory of one SM");
 
 struct WHParams {
     int N, UH, UW, UC, SC;
@@ -49,8 +96,13 @@ struct WHParams {
     float* ws;                 // [splits][9][UC][SC]
 };
 
+template <int STRIDE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmS,
                                                                       const WHParams p) {
+    typedef Geo<STRIDE> G;
+    typedef StageLayout<STRIDE> L;
+    constexpr int TH = G::TH;
+    constexpr uint32_t U_BYTES = L::U_BYTES, STAGE_BYTES = L::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -90,10 +142,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __gr
                 const int thi = rest % p.tiles_h, n = rest / p.tiles_h;
                 const int j0 = twi * TW, i0 = thi * TH;
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], U_BYTES + HW_ * HH_ * 128);
+                mbar_arrive_expect_tx(&full[stage], L::TX_BYTES);
                 uint8_t* sU = smem + stage * STAGE_BYTES;
                 tma_load_4d(sU, &tmU, &full[stage], ut * 64, j0, i0, n);                                   // rows/cols past the image read as zero
-                tma_load_4d(sU + U_BYTES, &tmS, &full[stage], st * 64, j0 - p.pad, i0 - p.pad, n);         // = the convolution's zero padding
+                if (STRIDE == 1) {
+                    tma_load_4d(sU + U_BYTES, &tmS, &full[stage], st * 64, j0 - p.pad, i0 - p.pad, n);     // = the convolution's zero padding
+                } else {
+#pragma unroll
+                    for (int pl = 0; pl < 4; pl++)                                                         // parity plane (pr, ps) = (pl >> 1, pl & 1)
+                        tma_load_4d(sU + U_BYTES + pl * G::PLANE_BYTES, &tmS, &full[stage], st * 64, 2 * j0 + (pl & 1), 2 * i0 + (pl >> 1), n);
+                }
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -104,7 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __gr
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(128, 64, 0, 1, 1);   // both operands MN-major
-            constexpr uint32_t pitch = HW_ * 128;                      // bytes between tile rows of the staged S footprint
+            constexpr uint32_t pitch = G::PW * 128;                    // bytes between tile rows of the staged S footprint
             int stage = 0;
             uint32_t phase = 0;
             bool first = true;
@@ -115,8 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __gr
                 const uint32_t s0 = u0 + U_BYTES;
 #pragma unroll
                 for (int pr = 0; pr < NPAIRS; pr++) {
-                    const int ta = 2 * pr, tb = (2 * pr + 1 < 9) ? 2 * pr + 1 : 2 * pr;
-                    const uint32_t offa = (uint32_t)((ta / 3) * HW_ + (ta % 3)) * 128u, offb = (uint32_t)((tb / 3) * HW_ + (tb % 3)) * 128u;
+                    const uint32_t offa = G::off_of(G::tap_of(2 * pr)), offb = G::off_of(G::tap_of((2 * pr + 1 < 9) ? 2 * pr + 1 : 2 * pr));
 #pragma unroll
                     for (int k = 0; k < TH / 2; k++)      // K = 16 pixels = two 8-pixel tile rows per MMA
                         umma_f16(tmem_base + pr * 64, umma_smem_desc(s0 + offa + (uint32_t)(2 * k) * pitch, offb - offa, pitch),
@@ -142,9 +199,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_wgrad_halo_kernel(const __gr
         tc_fence_after();
 #pragma unroll 1
         for (int pr = 0; pr < NPAIRS; pr++) {
-            const int tap = 2 * pr + member;
-            const bool valid = tap < 9;                       // the ninth tap is paired with itself: drop the copy
-            float* wp = p.ws + (((long long)split * 9 + (valid ? tap : 0)) * p.UC + ut * 64) * p.SC + s;
+            const bool valid = 2 * pr + member < 9;           // the ninth tap is paired with itself: drop the copy
+            const int tap = G::tap_of(valid ? 2 * pr + member : 8);
+            float* wp = p.ws + (((long long)split * 9 + tap) * p.UC + ut * 64) * p.SC + s;
 #pragma unroll 1
             for (int c = 0; c < 2; c++) {
                 uint32_t r[32];
@@ -169,7 +226,8 @@ struct WHPlan {
     int tiles_w, tiles_h, num_tiles, splits, u_tiles, s_tiles;
 };
 
-WHPlan make_plan(int N, int UH, int UW, int UC, int SC) {
+WHPlan make_plan(int N, int UH, int UW, int UC, int SC, int stride) {
+    const int TH = stride == 1 ? Geo<1>::TH : Geo<2>::TH;
     WHPlan pl;
     pl.tiles_w = (UW + TW - 1) / TW;
     pl.tiles_h = (UH + TH - 1) / TH;
@@ -177,8 +235,9 @@ WHPlan make_plan(int N, int UH, int UW, int UC, int SC) {
     pl.u_tiles = UC / 64;
     pl.s_tiles = SC / 64;
     const int col_tiles = pl.u_tiles * pl.s_tiles;
+    const int min_tiles = stride == 1 ? 4 : 8;      // pixel tiles per CTA that amortise the 9-tap epilogue (128 / 64 pixels per tile)
     int splits = gt_num_sms() / col_tiles;          // one CTA per SM (the accumulators take the whole TMEM)
-    if (splits > pl.num_tiles / 4) splits = pl.num_tiles / 4;   // at least four pixel tiles per CTA to amortise the 9-tap epilogue
+    if (splits > pl.num_tiles / min_tiles) splits = pl.num_tiles / min_tiles;
     if (t_wgrad_px_limit > 0) {                     // fp16x3 route: bound the accumulator updates per split-K slice (csrc/conv_f16x3.cu)
         const long long px = (long long)N * UH * UW;
         const int need = (int)((px + t_wgrad_px_limit - 1) / t_wgrad_px_limit);
@@ -190,26 +249,61 @@ WHPlan make_plan(int N, int UH, int UW, int UC, int SC) {
     return pl;
 }
 
-}  // namespace
-
-bool gt_wgrad_halo_applicable(int N, int UH, int UW, int UC, int SC, int SH, int SW, int KH, int KW, int stride, int pad) {
-    if (KH != 3 || KW != 3 || stride != 1 || pad < 0 || pad > 2) return false;
-    if (UC % 64 || SC % 64 || UH < TH || UW < TW || N < 1) return false;
-    if (SH != UH + 2 - 2 * pad || SW != UW + 2 - 2 * pad) return false;     // U = conv output of S (or S = transposed-conv output of U)
-    // worth it when the pixels dominate: enough tiles per CTA to amortise the 9-tap epilogue
-    WHPlan pl = make_plan(N, UH, UW, UC, SC);
-    return pl.num_tiles >= 32;
+template <int STRIDE>
+int launch(const CUtensorMap& tmU, const CUtensorMap& tmS, const WHParams& p, const WHPlan& pl, cudaStream_t stream) {
+    typedef StageLayout<STRIDE> L;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            gt_set_error("gt_conv2d_wgrad_f16 (halo): cannot reserve %u bytes of shared memory: %s", L::SMEM_TOTAL, cudaGetErrorString(e));
+            return -1;
+        }
+        configured = true;
+    }
+    dim3 grid((unsigned)pl.splits, (unsigned)(pl.u_tiles * pl.s_tiles), 1);
+    conv_wgrad_halo_kernel<STRIDE><<<grid, NTHREADS, L::SMEM_TOTAL, stream>>>(tmU, tmS, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        gt_set_error("gt_conv2d_wgrad_f16 (halo): CUDA launch failed: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return pl.splits;
 }
 
-long long gt_wgrad_halo_workspace(int N, int UH, int UW, int UC, int SC) {
-    WHPlan pl = make_plan(N, UH, UW, UC, SC);
+}  // namespace
+
+static int g_wgrad_halo_s2 = 1;        // 0: strided cases stay on the per-tap-row kernel (A/B switch, gt_conv_wgrad_config(2))
+void gt_wgrad_halo_enable_s2(int on) { g_wgrad_halo_s2 = on; }
+
+bool gt_wgrad_halo_applicable(int N, int UH, int UW, int UC, int SC, int SH, int SW, int KH, int KW, int stride, int pad) {
+    if (KH != 3 || KW != 3 || pad < 0 || N < 1 || UC % 64 || SC % 64) return false;
+    if (stride == 1) {
+        if (pad > 2 || UH < Geo<1>::TH || UW < TW) return false;
+        if (SH != UH + 2 - 2 * pad || SW != UW + 2 - 2 * pad) return false;     // U = conv output of S (or S = transposed-conv output of U)
+    } else if (stride == 2) {
+        // S is read at (2 i + r, 2 j + s), r, s in 0..2: the pad-0 down-convolution (S = x, 2 UH + 1 or 2 UH + 2 rows) and the pad-0
+        // transposed up-convolution (S = dy, 2 UH + 1 rows); rows / columns past S read as zero either way
+        if (!g_wgrad_halo_s2 || pad != 0 || UH < Geo<2>::TH || UW < TW) return false;
+        if (SH < 2 * UH + 1 || SH > 2 * UH + 2 || SW < 2 * UW + 1 || SW > 2 * UW + 2) return false;
+    } else {
+        return false;
+    }
+    // worth it when the pixels dominate: enough tiles per CTA to amortise the 9-tap epilogue
+    WHPlan pl = make_plan(N, UH, UW, UC, SC, stride);
+    return pl.num_tiles >= (stride == 1 ? 32 : 64);
+}
+
+long long gt_wgrad_halo_workspace(int N, int UH, int UW, int UC, int SC, int stride) {
+    WHPlan pl = make_plan(N, UH, UW, UC, SC, stride);
     return (long long)pl.splits * 9 * UC * SC;
 }
 
 // returns the number of splits written to the workspace (> 0) or a negative error indicator after gt_set_error
 int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n, long long ss_h,
-                         long long ss_w, int SH, int SW, int SC, int N, int pad, float* workspace, long long workspace_floats, cudaStream_t stream) {
-    WHPlan pl = make_plan(N, UH, UW, UC, SC);
+                         long long ss_w, int SH, int SW, int SC, int N, int stride, int pad, float* workspace, long long workspace_floats,
+                         cudaStream_t stream) {
+    WHPlan pl = make_plan(N, UH, UW, UC, SC, stride);
     if (workspace_floats < (long long)pl.splits * 9 * UC * SC) {
         gt_set_error("gt_conv2d_wgrad_f16 (halo): workspace too small");
         return -1;
@@ -223,7 +317,7 @@ int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long lon
     {
         cuuint64_t dims[4] = {(cuuint64_t)UC, (cuuint64_t)UW, (cuuint64_t)UH, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)us_w * 2, (cuuint64_t)us_h * 2, (cuuint64_t)us_n * 2};
-        cuuint32_t box[4] = {64, TW, TH, 1};
+        cuuint32_t box[4] = {64, TW, (cuuint32_t)(stride == 1 ? Geo<1>::TH : Geo<2>::TH), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmU, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(u), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -235,23 +329,16 @@ int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long lon
     {
         cuuint64_t dims[4] = {(cuuint64_t)SC, (cuuint64_t)SW, (cuuint64_t)SH, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)ss_w * 2, (cuuint64_t)ss_h * 2, (cuuint64_t)ss_n * 2};
-        cuuint32_t box[4] = {64, HW_, HH_, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        // stride 1: the whole 10 x 18 pixel footprint; stride 2: one 9 x 9 pixel parity plane per load (every other pixel / row of an
+        // 18 x 18 window: with element strides the box extent counts tensor elements, ceil(18 / 2) = 9 of them are written)
+        cuuint32_t box[4] = {64, (cuuint32_t)(stride == 1 ? Geo<1>::PW : 2 * Geo<2>::PW), (cuuint32_t)(stride == 1 ? Geo<1>::PH : 2 * Geo<2>::PH), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = encode(&tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             gt_set_error("gt_conv2d_wgrad_f16 (halo): S tensor map rejected (CUresult %d)", (int)r);
             return -1;
         }
-    }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
-        if (e != cudaSuccess) {
-            gt_set_error("gt_conv2d_wgrad_f16 (halo): cannot reserve %u bytes of shared memory: %s", SMEM_TOTAL, cudaGetErrorString(e));
-            return -1;
-        }
-        configured = true;
     }
     WHParams p;
     memset(&p, 0, sizeof(p));
@@ -267,12 +354,5 @@ int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long lon
     p.splits = pl.splits;
     p.s_tiles = pl.s_tiles;
     p.ws = workspace;
-    dim3 grid((unsigned)pl.splits, (unsigned)(pl.u_tiles * pl.s_tiles), 1);
-    conv_wgrad_halo_kernel<<<grid, NTHREADS, SMEM_TOTAL, stream>>>(tmU, tmS, p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        gt_set_error("gt_conv2d_wgrad_f16 (halo): CUDA launch failed: %s", cudaGetErrorString(e));
-        return -1;
-    }
-    return pl.splits;
+    return stride == 1 ? launch<1>(tmU, tmS, p, pl, stream) : launch<2>(tmU, tmS, p, pl, stream);
 }

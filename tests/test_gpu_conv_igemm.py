@@ -31,6 +31,12 @@ CASES = [
     ('3x3_T_s1_p1_64_128_40', 6, 64, 128, 40, 40, 3, 1, 1, True),
     ('3x3_p0_64_64_66', 4, 64, 64, 66, 66, 3, 1, 0, False),
     ('3x3_p1_256_256_32_n8', 8, 256, 256, 32, 32, 3, 1, 1, False),
+    # stride-2 / transposed stride-2 with enough pixels for the parity-plane staging of the halo wgrad kernel (>= 64 tiles of 8x8 output
+    # pixels), incl. even input sizes (2 OH + 2 rows), widths that are no multiple of 8 and tile rows past the image
+    ('3x3_s2_64_128_129_n4', 4, 64, 128, 129, 129, 3, 2, 0, False),
+    ('3x3_s2_128_64_66x90_n5', 5, 128, 64, 66, 90, 3, 2, 0, False),
+    ('3x3_T_s2_128_64_36x44_n3', 3, 128, 64, 36, 44, 3, 2, 0, True),
+    ('3x3_T_s2_256_128_32_n4', 4, 256, 128, 32, 32, 3, 2, 0, True),
 ]
 
 
