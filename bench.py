@@ -266,7 +266,7 @@ def hot_kernel_rooflines(device, pk):
 
     cfg = dict(output_padding=(0, 0), groups=1, stride=(1, 1), padding=(1, 1))
     for ci, co, r, tag in [(512, 512, 32, 'conv_igemm_halo2_kernel<256,1,10> (CTA pair)'), (256, 256, 64, 'conv_igemm_halo2_kernel<256,1,10> (CTA pair)'),
-                           (128, 128, 128, 'conv_igemm_halo2_kernel<128,2,12> (CTA pair)'), (64, 64, 256, 'conv_igemm_halo2_kernel<64,4,10> (CTA pair)')]:
+                           (128, 128, 128, 'conv_igemm_halo2_kernel<128,2,12> (CTA pair)'), (64, 64, 256, 'conv_rows_kernel (row streaming, N = 192)')]:
         xs = rot(lambda: t16([32, ci, r, r]), 32 * ci * r * r * 2 * 2)
         w = (torch.randn([co, ci, 3, 3], device=device) / (ci * 9) ** 0.5).to(torch.float16)
         pkd = conv_igemm.pack_weight(w, False)
@@ -274,7 +274,7 @@ def hot_kernel_rooflines(device, pk):
         ms = timeit([lambda x=x: conv_igemm.igemm_forward(x, w, transpose=False, packed=pkd, **cfg) for x in xs])
         add(f'conv_igemm_halo fwd 3x3 {ci}->{co} @{r}x{r}', tag, 'tensor', fl, ms)
         ms = timeit([lambda x=x: conv_igemm.igemm_wgrad(x, x, (co, ci, 3, 3), transpose=False, **cfg) for x in xs])
-        add(f'conv_wgrad_halo 3x3 {ci}x{co} over 32x{r}x{r} pixels', 'conv_wgrad_halo_kernel + wgrad_reduce_kernel', 'tensor', fl, ms)
+        add(f'conv_wgrad_halo 3x3 {ci}x{co} over 32x{r}x{r} pixels', 'conv_wgrad_halo_kernel<1> + wgrad_reduce_kernel', 'tensor', fl, ms)
         del xs
 
     f = upfirdn2d.setup_filter([1, 3, 3, 1], device=device)
