@@ -47,6 +47,9 @@ _PROTOTYPES = {
     'gt_modprep_gq': (_i, [_vp, _vp, _vp, _i, _vp]),
     'gt_modprep_style_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'gt_modprep_weight_bwd': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'gt_modprep_style_bwd2_a': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'gt_modprep_style_bwd2_b': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'gt_modprep_style_bwd2_c': (_i, [_vp] * 12 + [_i, _i, _i, _vp]),
     'gt_adam_chunk_bytes': (_i, []),
     'gt_adam_flat': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _vp]),
     'gt_ema_flat': (_i, [_vp, _vp, _ll, _f, _vp]),

@@ -15,8 +15,21 @@
 //     modprep_style_bwd    g_sn += 2 sn t;  gs = g_sn / m - [i = argmax] sign(s_i) (g_sn . sn) / m
 //     modprep_weight_bwd   g_wn = g_w + 2 wn g_wsq;  gW = a g_wn - [j = argmax] sign(W_j) (g_wn . W) a / m
 // (a = c / m the per-channel scale; without pre-normalisation a = 1 and the max terms vanish).  The max is taken at its
-// first occurrence; ties have measure zero for float weights / styles.  First-order only: the path-length pass, which
-// differentiates this backward, keeps the op-by-op form.
+// first occurrence; ties have measure zero for float weights / styles.
+//
+// Second order (the path-length regulariser differentiates the generator's backward, S3/training/loss.py:85-100).  The weight side is
+// never differentiated twice there (it is not on a path to the latents).  The style-side vector-Jacobian product
+//     (g_sn, g_d, s, wsq) -> gs          [with gq = -1/2 d^3 g_d,  gp = gq @ wsq,  tt = g_sn + 2 sn gp]
+// has, for a cotangent u of gs, the closed-form derivative (r = sign(s_k) u_k at the arg-max k, 0 without pre-normalisation; m = max|s|)
+//     v = u - r sn                      z = (v sn) @ wsq^T
+//     d/d g_sn = v / m                  d/d g_d = -d^3 z / m
+//     hq = 3/2 d^5 g_d z / m            hp = hq @ wsq
+//     D  = (2 gp v - r tt) / m + 2 sn hp
+//     d/d s = D / m + [i = k] sign(s_k) (-(tt . v) / m^2 - (D . sn) / m)
+//     d/d wsq = gq^T @ (2 v sn / m) + hq^T @ sn^2
+// evaluated by three small kernels (style_bwd2_a / _b / _c) around three calls of the fully-connected kernels (csrc/fc.cu) --
+// ~10 launches per layer instead of the ~70 autograd needs for the op-by-op chain.  Checked against autograd's double backward of the
+// tensor-op form in tests/test_gpu_modulated.py (and in float64 on the CPU: tests/test_modprep_closed_form.py).
 #include "gt_common.cuh"
 
 #include <cuda_fp16.h>
@@ -196,6 +209,77 @@ __global__ void __launch_bounds__(256) modprep_weight_bwd_kernel(const float* __
     }
 }
 
+
+// ---- second order of the style side (see the header) ------------------------------------------------------------------------------
+
+// grid = N.  u [N, I] -> v = u - r sn, vs = v sn, r [N]
+__global__ void __launch_bounds__(256) modprep_style_bwd2_a_kernel(const float* __restrict__ u, const float* __restrict__ sn, const int* __restrict__ sarg,
+                                                                    float* __restrict__ v, float* __restrict__ vs, float* __restrict__ r_out, int I, int prenorm) {
+    const int n = blockIdx.x;
+    const long long base = (long long)n * I;
+    float r = 0.f;
+    if (prenorm) {
+        const int k = sarg[n];
+        r = (sn[base + k] >= 0.f ? 1.f : -1.f) * u[base + k];
+    }
+    if (threadIdx.x == 0) r_out[n] = r;
+    for (int i = threadIdx.x; i < I; i += 256) {
+        const float x = sn[base + i];
+        const float vv = u[base + i] - r * x;
+        v[base + i] = vv;
+        vs[base + i] = vv * x;
+    }
+}
+
+// element-wise over [N, O]: ggd = -d^3 z / m, gq = -1/2 d^3 gd, hq = 3/2 d^5 gd z / m
+__global__ void modprep_style_bwd2_b_kernel(const float* __restrict__ d, const float* __restrict__ gd, const float* __restrict__ z, const float* __restrict__ smax,
+                                            float* __restrict__ ggd, float* __restrict__ gq, float* __restrict__ hq, int total, int O, int prenorm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float im = prenorm ? 1.f / smax[i / O] : 1.f;
+    const float dd = d[i], d3 = dd * dd * dd, g = gd[i], zz = z[i] * im;
+    ggd[i] = -d3 * zz;
+    gq[i] = -0.5f * d3 * g;
+    hq[i] = 1.5f * d3 * dd * dd * g * zz;
+}
+
+// grid = N.  -> gga = v / m (optional), g2s, x1 = 2 v sn / m, p = sn^2
+__global__ void __launch_bounds__(256) modprep_style_bwd2_c_kernel(const float* __restrict__ a, const float* __restrict__ sn, const float* __restrict__ gp,
+                                                                    const float* __restrict__ hp, const float* __restrict__ v, const float* __restrict__ r_in,
+                                                                    const float* __restrict__ smax, const int* __restrict__ sarg, float* __restrict__ gga,
+                                                                    float* __restrict__ g2s, float* __restrict__ x1, float* __restrict__ p_out, int I,
+                                                                    int prenorm) {
+    __shared__ float shs[8];
+    const int n = blockIdx.x;
+    const long long base = (long long)n * I;
+    const float m = prenorm ? smax[n] : 1.f, im = 1.f / m, r = r_in[n];
+    float L = 0.f, S2 = 0.f;
+    for (int i = threadIdx.x; i < I; i += 256) {
+        const float x = sn[base + i], g = gp[base + i], vv = v[base + i];
+        const float tt = (a ? a[base + i] : 0.f) + 2.f * x * g;
+        const float D = (2.f * g * vv - r * tt) * im + 2.f * x * hp[base + i];
+        L += tt * vv;
+        S2 += D * x;
+    }
+    if (prenorm) {
+        L = block_sum_fixed(L, shs);
+        S2 = block_sum_fixed(S2, shs);
+    }
+    const int k = prenorm ? sarg[n] : -1;
+    const float dm = -(L * im) * im - S2 * im;
+    for (int i = threadIdx.x; i < I; i += 256) {
+        const float x = sn[base + i], g = gp[base + i], vv = v[base + i];
+        const float tt = (a ? a[base + i] : 0.f) + 2.f * x * g;
+        const float D = (2.f * g * vv - r * tt) * im + 2.f * x * hp[base + i];
+        float out = D * im;
+        if (i == k) out += (x >= 0.f ? 1.f : -1.f) * dm;
+        g2s[base + i] = out;
+        if (gga) gga[base + i] = vv * im;
+        x1[base + i] = 2.f * vv * x * im;
+        p_out[base + i] = x * x;
+    }
+}
+
 }  // namespace
 
 extern "C" int gt_modprep_weight_fwd(const float* W, void* w16, float* wsq, float* scale, int* amax, int O, int I, int KK, int prenorm, void* stream) {
@@ -252,5 +336,37 @@ extern "C" int gt_modprep_weight_bwd(const float* W, const void* g_w, int g_w_dt
     else
         modprep_weight_bwd_kernel<float><<<O, 256, 0, st>>>(W, (const float*)g_w, g_wsq, scale, amax, gW, I, KK, prenorm ? 1 : 0);
     GT_CUDA_LAUNCH_CHECK("gt_modprep_weight_bwd");
+    return GT_OK;
+}
+
+// Second order of the style side, three stages around the fully-connected products (header of this file).  `sn` is the normalised style
+// (the style itself without pre-normalisation); gga may be NULL.
+extern "C" int gt_modprep_style_bwd2_a(const float* u, const float* sn, const int* sarg, float* v, float* vs, float* r, int N, int I, int prenorm, void* stream) {
+    GT_REQUIRE(u && sn && v && vs && r, "gt_modprep_style_bwd2_a: null pointer");
+    GT_REQUIRE(N > 0 && I > 0, "gt_modprep_style_bwd2_a: empty styles");
+    GT_REQUIRE(!prenorm || sarg, "gt_modprep_style_bwd2_a: pre-normalisation needs sarg");
+    modprep_style_bwd2_a_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(u, sn, sarg, v, vs, r, I, prenorm ? 1 : 0);
+    GT_CUDA_LAUNCH_CHECK("gt_modprep_style_bwd2_a");
+    return GT_OK;
+}
+
+extern "C" int gt_modprep_style_bwd2_b(const float* d, const float* gd, const float* z, const float* smax, float* ggd, float* gq, float* hq, int N, int O,
+                                       int prenorm, void* stream) {
+    GT_REQUIRE(d && gd && z && ggd && gq && hq, "gt_modprep_style_bwd2_b: null pointer");
+    GT_REQUIRE(N > 0 && O > 0, "gt_modprep_style_bwd2_b: empty");
+    GT_REQUIRE(!prenorm || smax, "gt_modprep_style_bwd2_b: pre-normalisation needs smax");
+    const int total = N * O;
+    modprep_style_bwd2_b_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d, gd, z, smax, ggd, gq, hq, total, O, prenorm ? 1 : 0);
+    GT_CUDA_LAUNCH_CHECK("gt_modprep_style_bwd2_b");
+    return GT_OK;
+}
+
+extern "C" int gt_modprep_style_bwd2_c(const float* a, const float* sn, const float* gp, const float* hp, const float* v, const float* r, const float* smax,
+                                       const int* sarg, float* gga, float* g2s, float* x1, float* p, int N, int I, int prenorm, void* stream) {
+    GT_REQUIRE(sn && gp && hp && v && r && g2s && x1 && p, "gt_modprep_style_bwd2_c: null pointer");
+    GT_REQUIRE(N > 0 && I > 0, "gt_modprep_style_bwd2_c: empty styles");
+    GT_REQUIRE(!prenorm || (smax && sarg), "gt_modprep_style_bwd2_c: pre-normalisation needs smax and sarg");
+    modprep_style_bwd2_c_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(a, sn, gp, hp, v, r, smax, sarg, gga, g2s, x1, p, I, prenorm ? 1 : 0);
+    GT_CUDA_LAUNCH_CHECK("gt_modprep_style_bwd2_c");
     return GT_OK;
 }

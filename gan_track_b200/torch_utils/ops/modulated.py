@@ -258,98 +258,231 @@ def prep_tensor_ops(weight, styles, prenorm):
     return (weight.to(torch.float16), styles, d) if prenorm else (None, None, d)
 
 
+fused_prep = True          # False: callers keep the tensor-op chain (tests compare the two routes)
+# which form evaluated the second-order pass of the style side (tests assert the path-length pattern stays on the closed form)
+prep_stats = {'style_bwd2_closed_form': 0, 'style_bwd2_autograd': 0}
+
+
 def prep_applicable(weight, styles):
-    """The fused kernels implement the first derivative; under `create_graph` `_ModPrep.backward` switches to the tensor-op form
-    (`prep_tensor_ops`), so the op is closed under differentiation wherever it is used.  The path-length pass, which always
-    differentiates this backward, skips the detour and uses the tensor-op form directly (`rgb.op_by_op_torgb`, a speed switch,
-    not a correctness one)."""
-    from . import rgb
-    return (rgb.torgb_fused and weight.is_cuda and weight.dtype == torch.float32 and styles.dtype == torch.float32 and styles.ndim == 2
+    """The fused route is closed under differentiation to second order in the styles (what the path-length pass needs: closed-form
+    kernels, `_PrepStyleGrad.backward`) and falls back to autograd over the tensor-op form for anything beyond (a cotangent on the
+    weight-side gradient, third order), so it is used wherever the shapes fit."""
+    return (fused_prep and weight.is_cuda and weight.dtype == torch.float32 and styles.dtype == torch.float32 and styles.ndim == 2
             and weight.ndim == 4 and 1 <= styles.shape[0] <= 64 and weight.shape[1] % 4 == 0 and styles.shape[1] == weight.shape[1])
 
 
-class _ModPrep(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, weight, styles, prenorm):
-        from . import fc
-        lib = _lib.load()
-        O, I, kh, kw = weight.shape
-        N = styles.shape[0]
-        W, s = weight.contiguous(), styles.contiguous()
-        dev = W.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        wsq, sn2 = torch.empty([O, I], **f32), torch.empty([N, I], **f32)
-        w16 = scale = amax = smax = sarg = None
-        sn = s
-        if prenorm:
-            w16 = torch.empty([O, I, kh, kw], dtype=torch.float16, device=dev)
-            scale, smax = torch.empty([O], **f32), torch.empty([N], **f32)
-            amax, sarg = torch.empty([O], dtype=torch.int32, device=dev), torch.empty([N], dtype=torch.int32, device=dev)
-            sn = torch.empty([N, I], **f32)
-        with torch.cuda.device(dev):
-            st = _lib.stream_of(W)
-            _lib.check(lib.gt_modprep_weight_fwd(_lib.ptr(W), _lib.ptr(w16), _lib.ptr(wsq), _lib.ptr(scale), _lib.ptr(amax), O, I, kh * kw, int(prenorm), st),
-                       'gt_modprep_weight_fwd')
-            _lib.check(lib.gt_modprep_style_fwd(_lib.ptr(s), _lib.ptr(sn) if prenorm else None, _lib.ptr(sn2), _lib.ptr(smax), _lib.ptr(sarg), N, I,
-                                                int(prenorm), st), 'gt_modprep_style_fwd')
-            q = fc._fwd(sn2, wsq, None, 1.0, 0.0)                                # [N, O]
-            d = torch.empty_like(q)
-            _lib.check(lib.gt_modprep_rsqrt(_lib.ptr(q), _lib.ptr(d), N * O, 1e-8, st), 'gt_modprep_rsqrt')
-        _lib.count_launch(3)
-        ctx.save_for_backward(W, sn, sn2, wsq, d, scale, amax, smax, sarg, weight, styles)
-        ctx.prenorm = bool(prenorm)
-        ctx.wshape = weight.shape
-        return (w16, sn, d) if prenorm else (None, None, d)
+def _weight_chain(weight, prenorm):
+    """Weight side of `prep_tensor_ops`: (scaled fp16 weight | None, wsq [O, I])."""
+    if prenorm:
+        fan_in = weight.shape[1] * weight.shape[2] * weight.shape[3]
+        weight = weight * (1 / np.sqrt(fan_in) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+    wsq = weight.square().sum(dim=[2, 3])
+    return (weight.to(torch.float16) if prenorm else None), wsq
+
+
+def _style_chain(styles, wsq, prenorm):
+    """Style side of `prep_tensor_ops`: (normalised styles | the styles, dcoefs [N, O])."""
+    sn = styles / styles.norm(float('inf'), dim=1, keepdim=True) if prenorm else styles
+    return sn, (sn.square() @ wsq.t() + 1e-8).rsqrt()
+
+
+def _leaf(t):
+    return t.detach().requires_grad_(True)
+
+
+class _PrepWeight(torch.autograd.Function):
+    """weight [O,I,kh,kw] fp32 -> (fp16 pre-normalised weight | empty, wsq [O,I]); csrc/modprep.cu, first-order kernels.  The path-length
+    pass never differentiates this backward (the weight is not on a path to the latents); if some other caller does, the backward is
+    evaluated through autograd on the tensor-op form."""
 
     @staticmethod
-    def backward(ctx, g_w, g_sn, g_d):
+    def forward(ctx, weight, prenorm):
+        lib = _lib.load()
+        O, I, kh, kw = weight.shape
+        W = weight.contiguous()
+        dev = W.device
+        wsq = torch.empty([O, I], dtype=torch.float32, device=dev)
+        w16 = scale = amax = None
+        if prenorm:
+            w16 = torch.empty([O, I, kh, kw], dtype=torch.float16, device=dev)
+            scale = torch.empty([O], dtype=torch.float32, device=dev)
+            amax = torch.empty([O], dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gt_modprep_weight_fwd(_lib.ptr(W), _lib.ptr(w16), _lib.ptr(wsq), _lib.ptr(scale), _lib.ptr(amax), O, I, kh * kw, int(prenorm),
+                                                 _lib.stream_of(W)), 'gt_modprep_weight_fwd')
+        _lib.count_launch()
+        ctx.save_for_backward(W, scale, amax, weight)
+        ctx.prenorm = bool(prenorm)
+        ctx.set_materialize_grads(False)
+        if w16 is None:
+            w16 = torch.empty([0], dtype=torch.float16, device=dev)
+            ctx.mark_non_differentiable(w16)
+        return w16, wsq
+
+    @staticmethod
+    def backward(ctx, g_w, g_wsq):
+        W, scale, amax, weight_in = ctx.saved_tensors
+        if not ctx.needs_input_grad[0] or (g_w is None and g_wsq is None):
+            return None, None
+        if torch.is_grad_enabled():          # only inside backward(create_graph=True) with the weight on the differentiated path
+            with torch.enable_grad():
+                wi = weight_in if weight_in.requires_grad else _leaf(weight_in)
+                w16, wsq = _weight_chain(wi, ctx.prenorm)
+                pairs = [(o, g) for o, g in ((w16, g_w if ctx.prenorm else None), (wsq, g_wsq)) if o is not None and g is not None]
+                gW, = torch.autograd.grad([o for o, _ in pairs], [wi], [g.to(o.dtype) for o, g in pairs], create_graph=True)
+            return gW, None
+        O, I, kh, kw = W.shape
+        if g_wsq is None:
+            g_wsq = torch.zeros([O, I], dtype=torch.float32, device=W.device)
+        g_wsq = g_wsq.contiguous().to(torch.float32)
+        g_w = g_w.contiguous() if (g_w is not None and ctx.prenorm) else None
+        gW = torch.empty_like(W)
+        with torch.cuda.device(W.device):
+            _lib.check(_lib.load().gt_modprep_weight_bwd(_lib.ptr(W), _lib.ptr(g_w), _lib.dtype_code(g_w) if g_w is not None else 0, _lib.ptr(g_wsq),
+                                                         _lib.ptr(scale), _lib.ptr(amax), _lib.ptr(gW), O, I, kh * kw, int(ctx.prenorm), _lib.stream_of(W)),
+                       'gt_modprep_weight_bwd')
+        _lib.count_launch()
+        return gW, None
+
+
+class _PrepStyle(torch.autograd.Function):
+    """(styles [N,I], wsq [O,I]) -> (normalised styles | empty, dcoefs [N,O]); backward = `_PrepStyleGrad`, itself differentiable."""
+
+    @staticmethod
+    def forward(ctx, styles, wsq, prenorm):
         from . import fc
         lib = _lib.load()
-        W, sn, sn2, wsq, d, scale, amax, smax, sarg, weight_in, styles_in = ctx.saved_tensors
-        if torch.is_grad_enabled():          # only true inside backward(create_graph=True)
-            # create_graph: someone will differentiate this backward -> evaluate it as the vector-Jacobian product of the
-            # tensor-op form, which autograd can differentiate again (w.r.t. the incoming gradients, the weight and the styles)
-            with torch.enable_grad():
-                wi = weight_in if weight_in.requires_grad else weight_in.detach().requires_grad_(True)
-                si = styles_in if styles_in.requires_grad else styles_in.detach().requires_grad_(True)
-                outs = prep_tensor_ops(wi, si, ctx.prenorm)
-                pairs = [(o, g) for o, g in zip(outs, (g_w, g_sn, g_d)) if o is not None and g is not None]
-                want = [t for t, need in ((wi, ctx.needs_input_grad[0]), (si, ctx.needs_input_grad[1])) if need]
-                got = list(torch.autograd.grad([o for o, _ in pairs], want, [g.to(o.dtype) for o, g in pairs], create_graph=True, allow_unused=True))
-            gW2 = got.pop(0) if ctx.needs_input_grad[0] else None
-            gs2 = got.pop(0) if ctx.needs_input_grad[1] else None
-            return gW2, gs2, None
-        O, I, kh, kw = ctx.wshape
-        N = sn.shape[0]
+        s, wsq_c = styles.contiguous(), wsq.contiguous()
+        N, I = s.shape
+        dev = s.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        sn2 = torch.empty([N, I], **f32)
+        smax = sarg = None
+        sn = s
+        if prenorm:
+            sn = torch.empty([N, I], **f32)
+            smax = torch.empty([N], **f32)
+            sarg = torch.empty([N], dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_of(s)
+            _lib.check(lib.gt_modprep_style_fwd(_lib.ptr(s), _lib.ptr(sn) if prenorm else None, _lib.ptr(sn2), _lib.ptr(smax), _lib.ptr(sarg), N, I,
+                                                int(prenorm), st), 'gt_modprep_style_fwd')
+            q = fc._fwd(sn2, wsq_c, None, 1.0, 0.0)                                # [N, O]
+            d = torch.empty_like(q)
+            _lib.check(lib.gt_modprep_rsqrt(_lib.ptr(q), _lib.ptr(d), q.numel(), 1e-8, st), 'gt_modprep_rsqrt')
+        _lib.count_launch(2)
+        ctx.save_for_backward(styles, wsq, sn, sn2, smax, sarg, d)
+        ctx.prenorm = bool(prenorm)
+        ctx.set_materialize_grads(False)
+        if prenorm:
+            return sn, d
+        empty = torch.empty([0], **f32)
+        ctx.mark_non_differentiable(empty)
+        return empty, d
+
+    @staticmethod
+    def backward(ctx, g_sn, g_d):
+        styles, wsq, sn, sn2, smax, sarg, d = ctx.saved_tensors
+        if not ctx.prenorm:
+            g_sn = None
+        if g_sn is None and g_d is None:
+            return None, None, None
         if g_d is None:
             g_d = torch.zeros_like(d)
+        gs, g_wsq = _PrepStyleGrad.apply(g_sn, g_d, styles, wsq, sn, sn2, smax, sarg, d, ctx.prenorm)
+        return (gs if ctx.needs_input_grad[0] else None), (g_wsq if ctx.needs_input_grad[1] else None), None
+
+
+class _PrepStyleGrad(torch.autograd.Function):
+    """(g_sn | None, g_d, styles, wsq) -> (gs, g_wsq): the first-order vector-Jacobian product of `_PrepStyle` on the fused kernels.  Its own
+    backward (a cotangent on gs: the path-length pass) is closed form, csrc/modprep.cu `style_bwd2_*`."""
+
+    @staticmethod
+    def forward(ctx, g_sn, g_d, styles, wsq, sn, sn2, smax, sarg, d, prenorm):
+        from . import fc
+        lib = _lib.load()
+        N, I = sn.shape
         g_d = g_d.contiguous().to(torch.float32)
+        g_sn = g_sn.contiguous().to(torch.float32) if g_sn is not None else None
+        wsq_c = wsq.contiguous()
         gq = torch.empty_like(d)
-        gW = gs = None
-        with torch.cuda.device(W.device):
-            st = _lib.stream_of(W)
-            _lib.check(lib.gt_modprep_gq(_lib.ptr(d), _lib.ptr(g_d), _lib.ptr(gq), N * O, st), 'gt_modprep_gq')
-            _lib.count_launch()
-            if ctx.needs_input_grad[1]:
-                t = fc._dgrad(gq, wsq, 1.0)                                      # [N, I]
-                g_sn = g_sn.contiguous().to(torch.float32) if g_sn is not None else None
-                gs = torch.empty_like(sn)
-                _lib.check(lib.gt_modprep_style_bwd(_lib.ptr(g_sn), _lib.ptr(sn), _lib.ptr(t), _lib.ptr(smax), _lib.ptr(sarg), _lib.ptr(gs), N, I,
-                                                    int(ctx.prenorm), st), 'gt_modprep_style_bwd')
-                _lib.count_launch()
-            if ctx.needs_input_grad[0]:
-                g_wsq = fc._wgrad(gq, sn2, 1.0, 0.0, False)[0]                   # [O, I]
-                g_w = g_w.contiguous() if g_w is not None else None
-                gW = torch.empty_like(W)
-                _lib.check(lib.gt_modprep_weight_bwd(_lib.ptr(W), _lib.ptr(g_w), _lib.dtype_code(g_w) if g_w is not None else 0, _lib.ptr(g_wsq),
-                                                     _lib.ptr(scale), _lib.ptr(amax), _lib.ptr(gW), O, I, kh * kw, int(ctx.prenorm), st), 'gt_modprep_weight_bwd')
-                _lib.count_launch()
-                gW = gW.reshape(ctx.wshape)
-        return gW, gs, None
+        gs = torch.empty_like(sn)
+        with torch.cuda.device(sn.device):
+            st = _lib.stream_of(sn)
+            _lib.check(lib.gt_modprep_gq(_lib.ptr(d), _lib.ptr(g_d), _lib.ptr(gq), d.numel(), st), 'gt_modprep_gq')
+            gp = fc._dgrad(gq, wsq_c, 1.0)                                         # [N, I]
+            _lib.check(lib.gt_modprep_style_bwd(_lib.ptr(g_sn), _lib.ptr(sn), _lib.ptr(gp), _lib.ptr(smax), _lib.ptr(sarg), _lib.ptr(gs), N, I, int(prenorm), st),
+                       'gt_modprep_style_bwd')
+            g_wsq = fc._wgrad(gq, sn2, 1.0, 0.0, False)[0]                         # [O, I]
+        _lib.count_launch(2)
+        ctx.save_for_backward(g_sn, g_d, styles, wsq, sn, sn2, smax, sarg, d, gp)
+        ctx.prenorm = bool(prenorm)
+        ctx.set_materialize_grads(False)         # an unused g_wsq must arrive as None in backward, not as a tensor of zeros
+        return gs, g_wsq
+
+    @staticmethod
+    def backward(ctx, u, V):
+        from . import fc
+        g_sn, g_d, styles, wsq, sn, sn2, smax, sarg, d, gp = ctx.saved_tensors
+        prenorm = ctx.prenorm
+        need = ctx.needs_input_grad
+        none6 = (None,) * 6
+        if u is None and V is None:
+            return (None, None, None, None) + none6
+        if V is not None or torch.is_grad_enabled():
+            # beyond what the closed form covers (cotangent on the weight-side gradient, third order): autograd over the tensor-op form
+            prep_stats['style_bwd2_autograd'] += 1
+            with torch.enable_grad():
+                a = _leaf(g_sn) if g_sn is not None else None
+                b, s_, w_ = _leaf(g_d), _leaf(styles), _leaf(wsq)
+                o_sn, o_d = _style_chain(s_, w_, prenorm)
+                outs, cots = ([o_sn, o_d], [a, b]) if a is not None else ([o_d], [b])
+                gs_, gw_ = torch.autograd.grad(outs, [s_, w_], cots, create_graph=True)
+                pairs = [(o, c) for o, c in ((gs_, u), (gw_, V)) if c is not None]
+                wrt = [t for t in (a, b, s_, w_) if t is not None]
+                got = list(torch.autograd.grad([o for o, _ in pairs], wrt, [c for _, c in pairs], allow_unused=True))
+            gga = got.pop(0) if a is not None else None
+            ggb, g2s, g2w = got
+            return (gga if need[0] else None, ggb if need[1] else None, g2s if need[2] else None, g2w if need[3] else None) + none6
+        prep_stats['style_bwd2_closed_form'] += 1
+        lib = _lib.load()
+        N, I = sn.shape
+        O = d.shape[1]
+        dev = sn.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        u = u.contiguous().to(torch.float32)
+        wsq_c = wsq.contiguous()
+        v, vs, r = torch.empty([N, I], **f32), torch.empty([N, I], **f32), torch.empty([N], **f32)
+        ggd = torch.empty([N, O], **f32)
+        g2 = torch.empty([2 * N, O], **f32)            # rows [gq ; hq]
+        x2 = torch.empty([2 * N, I], **f32)            # rows [2 v sn / m ; sn^2]
+        gga = torch.empty([N, I], **f32) if (g_sn is not None and need[0]) else None
+        g2s = torch.empty([N, I], **f32)
+        with torch.cuda.device(dev):
+            st = _lib.stream_of(sn)
+            _lib.check(lib.gt_modprep_style_bwd2_a(_lib.ptr(u), _lib.ptr(sn), _lib.ptr(sarg), _lib.ptr(v), _lib.ptr(vs), _lib.ptr(r), N, I, int(prenorm), st),
+                       'gt_modprep_style_bwd2_a')
+            z = fc._fwd(vs, wsq_c, None, 1.0, 0.0)                                 # [N, O]
+            _lib.check(lib.gt_modprep_style_bwd2_b(_lib.ptr(d), _lib.ptr(g_d), _lib.ptr(z), _lib.ptr(smax), _lib.ptr(ggd), _lib.ptr(g2[:N]), _lib.ptr(g2[N:]),
+                                                   N, O, int(prenorm), st), 'gt_modprep_style_bwd2_b')
+            hp = fc._dgrad(g2[N:], wsq_c, 1.0)                                     # [N, I]
+            _lib.check(lib.gt_modprep_style_bwd2_c(_lib.ptr(g_sn), _lib.ptr(sn), _lib.ptr(gp), _lib.ptr(hp), _lib.ptr(v), _lib.ptr(r), _lib.ptr(smax),
+                                                   _lib.ptr(sarg), _lib.ptr(gga), _lib.ptr(g2s), _lib.ptr(x2[:N]), _lib.ptr(x2[N:]), N, I, int(prenorm), st),
+                       'gt_modprep_style_bwd2_c')
+            g2w = None
+            if need[3]:
+                if 2 * N <= 64:
+                    g2w = fc._wgrad(g2, x2, 1.0, 0.0, False)[0]                    # gq^T @ x1 + hq^T @ sn^2 in one product over 2N rows
+                else:
+                    g2w = fc._wgrad(g2[:N], x2[:N], 1.0, 0.0, False)[0] + fc._wgrad(g2[N:], x2[N:], 1.0, 0.0, False)[0]
+        _lib.count_launch(3)
+        return (gga, ggd if need[1] else None, g2s if need[2] else None, g2w) + none6
 
 
 def prep(weight, styles, prenorm):
     """(weight_scaled_fp16 | None, styles_normalised | None, dcoefs): the pre-normalised operands (fp16 layers) and the
-    demodulation coefficients of modulated_conv2d (S3/training/networks_stylegan2.py:52-63), differentiable once w.r.t. weight
-    and styles."""
-    return _ModPrep.apply(weight, styles, bool(prenorm))
+    demodulation coefficients of modulated_conv2d (S3/training/networks_stylegan2.py:52-63), differentiable w.r.t. weight
+    and styles; twice in the styles on the fused kernels."""
+    w16, wsq = _PrepWeight.apply(weight, bool(prenorm))
+    sn, d = _PrepStyle.apply(styles, wsq, bool(prenorm))
+    return (w16, sn, d) if prenorm else (None, None, d)

@@ -187,6 +187,14 @@ int gt_modprep_style_bwd(const float* g_sn, const float* sn, const float* t, con
                          void* stream);
 int gt_modprep_weight_bwd(const float* W, const void* g_w, int g_w_dtype, const float* g_wsq, const float* scale, const int* amax, float* gW, int O, int I,
                           int KK, int prenorm, void* stream);
+/* Second order of the style side (the path-length pass differentiates the generator's backward): three stages around gt_fc_* products,
+ * formulas in csrc/modprep.cu.  gt_modprep_style_bwd2_a: v = u - r sn, vs = v sn, r;  _b: ggd, gq, hq from d, gd, z = vs @ wsq^T;
+ * _c: gga (may be NULL), g2s, x1 = 2 v sn / m, p = sn^2 from a = g_sn (may be NULL), gp = gq @ wsq, hp = hq @ wsq. */
+int gt_modprep_style_bwd2_a(const float* u, const float* sn, const int* sarg, float* v, float* vs, float* r, int N, int I, int prenorm, void* stream);
+int gt_modprep_style_bwd2_b(const float* d, const float* gd, const float* z, const float* smax, float* ggd, float* gq, float* hq, int N, int O, int prenorm,
+                            void* stream);
+int gt_modprep_style_bwd2_c(const float* a, const float* sn, const float* gp, const float* hp, const float* v, const float* r, const float* smax,
+                            const int* sarg, float* gga, float* g2s, float* x1, float* p, int N, int I, int prenorm, void* stream);
 
 /* ---- training batches from a device-resident packed shard ---------------------------------
  * One launch replaces the reference's per-iteration DataLoader work (unzip + unpickle per slice,

@@ -172,42 +172,67 @@ def test_modprep_matches_tensor_ops(N, O, I, k, prenorm):
     gW2, gs2 = torch.autograd.grad([d], [weight, styles], [g_d])
     rW2, rgs2 = torch.autograd.grad([_ref_prep(weight, styles, prenorm)[2]], [weight, styles], [g_d])
     assert _rel(gW2, rW2) <= 1e-5 and _rel(gs2, rgs2) <= 1e-5
-    # closed under differentiation: under create_graph the backward switches to the tensor-op form, so a second-order use of
-    # the fused op (any regulariser / metric that differentiates G's backward outside the path-length switch) matches the chain
-    w16, sn, d = modulated.prep(weight, styles, prenorm)
-    probe = torch.randn_like(d)
-    g, = torch.autograd.grad([(d * probe).sum()], [styles], create_graph=True)
-    gg_w, gg_s = torch.autograd.grad(g.square().sum(), [weight, styles])
-    rd2 = _ref_prep(weight, styles, prenorm)[2]
-    rg, = torch.autograd.grad([(rd2 * probe).sum()], [styles], create_graph=True)
-    rgg_w, rgg_s = torch.autograd.grad(rg.square().sum(), [weight, styles])
+    # closed under differentiation to second order (the path-length pass differentiates G's backward, S3/training/loss.py:85-100):
+    # the style side's backward has a closed-form backward of its own (csrc/modprep.cu style_bwd2_*), checked against autograd's double
+    # backward of the tensor-op chain -- with every output used non-linearly, as mod_scale / demod_act use them
+    def second_order(prep_fn):
+        w16, sn, d = prep_fn(weight, styles, prenorm)
+        probe_d = torch.randn(d.shape, device='cuda', generator=torch.Generator('cuda').manual_seed(3))
+        y = (d * probe_d).sum() + (d.square() * probe_d.flip(0)).sum()
+        if prenorm:
+            probe_s = torch.randn(sn.shape, device='cuda', generator=torch.Generator('cuda').manual_seed(4))
+            y = y + (sn * probe_s).sum() + (sn.square() * probe_s.flip(1)).sum() + (sn[:, :8].sum(1, keepdim=True) * d).sum()
+        g, = torch.autograd.grad([y], [styles], create_graph=True)
+        gg_w, gg_s = torch.autograd.grad(g.square().sum(), [weight, styles])
+        return g.detach(), gg_w, gg_s
+    before, stats0 = _lib_launches(), dict(modulated.prep_stats)
+    g, gg_w, gg_s = second_order(modulated.prep)
+    used = _lib_launches() - before
+    assert modulated.prep_stats['style_bwd2_closed_form'] == stats0['style_bwd2_closed_form'] + 1
+    assert modulated.prep_stats['style_bwd2_autograd'] == stats0['style_bwd2_autograd']
+    rg, rgg_w, rgg_s = second_order(_ref_prep)
     assert _rel(g, rg) <= 1e-5 and _rel(gg_w, rgg_w) <= 1e-4 and _rel(gg_s, rgg_s) <= 1e-4, (_rel(g, rg), _rel(gg_w, rgg_w), _rel(gg_s, rgg_s))
+    assert used <= 24, f'{used} launches: the second-order pass must stay on the fused kernels'
+    # a cotangent on the weight-side gradient (double backward w.r.t. the weight) takes the autograd fallback and still matches
+    def second_order_w(prep_fn):
+        w16, sn, d = prep_fn(weight, styles, prenorm)
+        y = (d * torch.linspace(-1, 1, d.numel(), device='cuda').reshape(d.shape)).sum()
+        gw, gs_ = torch.autograd.grad([y], [weight, styles], create_graph=True)
+        return torch.autograd.grad(gw.square().sum() + gs_.square().sum(), [weight, styles])
+    stats0 = dict(modulated.prep_stats)
+    a_w, a_s = second_order_w(modulated.prep)
+    assert modulated.prep_stats['style_bwd2_autograd'] == stats0['style_bwd2_autograd'] + 1
+    b_w, b_s = second_order_w(_ref_prep)
+    assert _rel(a_w, b_w) <= 1e-4 and _rel(a_s, b_s) <= 1e-4, (_rel(a_w, b_w), _rel(a_s, b_s))
+    # the path-length switch no longer changes the route (it only concerns the fused ToRGB)
     from gan_track_b200.torch_utils.ops import rgb
     with rgb.op_by_op_torgb():
-        assert not modulated.prep_applicable(weight, styles)
+        assert modulated.prep_applicable(weight, styles)
+
+
+def _lib_launches():
+    from gan_track_b200 import _lib
+    return _lib.launches
 
 
 @pytest.mark.parametrize('dtype,C', [(torch.float16, 64), (torch.float32, 32)])
 def test_modulated_conv2d_prep_route_equals_op_chain(dtype, C):
-    """modulated_conv2d through the fused preparation vs the tensor-op chain (selected by the path-length switch): output and
+    """modulated_conv2d through the fused preparation vs the tensor-op chain (`modulated.fused_prep = False`): output and
     the gradients of x, weight, styles."""
-    from gan_track_b200.torch_utils.ops import rgb
     from gan_track_b200.training import networks_stylegan2 as nets
     torch.manual_seed(7)
     x = _cl(torch.randn(4, C, 32, 32, device='cuda').to(dtype)).requires_grad_(True)
     weight = torch.randn(2 * C, C, 3, 3, device='cuda').requires_grad_(True)
     styles = (torch.randn(4, C, device='cuda') + 1).requires_grad_(True)
     noise = torch.randn(4, 1, 32, 32, device='cuda')
+    from gan_track_b200.torch_utils.ops import modulated
     res = []
     for fused in (True, False):
-        ctx = rgb.op_by_op_torgb() if not fused else None
-        if ctx is not None:
-            ctx.__enter__()
+        modulated.fused_prep = fused
         try:
             y = nets.modulated_conv2d(x, weight, styles, noise=noise, padding=1, fused_modconv=False)
         finally:
-            if ctx is not None:
-                ctx.__exit__()
+            modulated.fused_prep = True
         dy = torch.randn(y.shape, device='cuda', generator=torch.Generator('cuda').manual_seed(1)).to(dtype)
         res.append((y.detach(),) + torch.autograd.grad(y, [x, weight, styles], dy))
     tol = 1e-2 if dtype == torch.float16 else 1e-5
