@@ -115,12 +115,17 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             want_dx, want_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
             if not (want_dx or want_db):
                 return None, None
-            fusable = (want_db and not torch.is_grad_enabled() and act in ('linear', 'lrelu') and not trivial
+            fusable = (want_db and act in ('linear', 'lrelu') and not trivial
                        and dy.dtype in (torch.float16, torch.float32) and dy.numel() > 0
                        and (dy.stride(dim) == 1 or dy.is_contiguous()))
-            if fusable:
+            if fusable and not torch.is_grad_enabled():
                 dx, db = _fused_bwd(dy, y if y.numel() else None, dim, spec, alpha, gain, clamp)
                 return dx, db
+            if fusable:
+                # under create_graph (R1 differentiates the discriminator's backward, S3/training/loss.py:120-133) the same fused pass as a
+                # differentiable Function: the bias gradient is never used by that pass, and `dx.sum(...)` over the activation tensor
+                # (what the reference runs, OPS/bias_act.py:169-170) would cost as much as the gradient itself
+                return BiasActCudaGradFused.apply(dy, y)
             dx = dy
             if not trivial:
                 dx = BiasActCudaGrad.apply(dy, x, b, y)
@@ -148,6 +153,30 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             if spec.has_2nd_grad and ctx.needs_input_grad[2]:
                 d_b = d_x.sum([i for i in range(d_x.ndim) if i != dim])
             return d_dy, d_x, d_b, None
+
+    class BiasActCudaGradFused(torch.autograd.Function):
+        """(dy, y) -> (dx, db) in one pass for linear / lrelu (no second derivative of the activation): dx = dy * slope(y), db = sum dx.  Its
+        backward is the gradient Function again, applied to d_dx + d_db (broadcast)."""
+
+        @staticmethod
+        def forward(ctx, dy, y):
+            ctx.memory_format = _mem_format(dy)
+            dx, db = _fused_bwd(dy, y if y.numel() else None, dim, spec, alpha, gain, clamp)
+            ctx.save_for_backward(y)
+            ctx.dx_shape, ctx.dx_dtype = tuple(dy.shape), dy.dtype
+            ctx.set_materialize_grads(False)
+            return dx, db
+
+        @staticmethod
+        def backward(ctx, d_dx, d_db):
+            y, = ctx.saved_tensors
+            if not ctx.needs_input_grad[0] or (d_dx is None and d_db is None):
+                return None, None
+            t = d_dx.contiguous(memory_format=ctx.memory_format) if d_dx is not None else None
+            if d_db is not None:
+                bb = d_db.to(ctx.dx_dtype).reshape([-1 if i == dim else 1 for i in range(len(ctx.dx_shape))])
+                t = (t + bb) if t is not None else bb.expand(ctx.dx_shape).contiguous(memory_format=ctx.memory_format)
+            return BiasActCudaGrad.apply(t, _empty, _empty, y), None
 
     BiasActCuda.Grad = BiasActCudaGrad          # used by the fused conv + bias_act op (conv2d_gradfix.conv2d_bias_act)
     BiasActCuda.cfg = (spec, alpha, gain, clamp, trivial)

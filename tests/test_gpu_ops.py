@@ -88,6 +88,30 @@ def test_bias_act_path_cases(golden, case, cl, dtype):
         assert_close(d_dy, ref, TOL[dtype], 'd_dy')
 
 
+@pytest.mark.parametrize('dtype,cl', [(torch.float32, False), (torch.float16, True)])
+def test_bias_act_fused_grad_is_differentiable_through_db(dtype, cl):
+    """Under create_graph the backward is ONE fused (dx, db) pass (R1 never uses db, and `dx.sum` over the activation would cost a pass of
+    its own); it stays differentiable: d<dx, v> + <db, u> / d(dy) = slope(y) * (v + u[c])."""
+    torch.manual_seed(5)
+    x = torch.randn(3, 16, 9, 7, device=DEV).to(dtype)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    b = torch.randn(16, device=DEV).to(dtype).requires_grad_(True)
+    y = bias_act.bias_act(x, b, act='lrelu', clamp=1.5)
+    dy = torch.randn_like(y).requires_grad_(True)
+    dx, db = torch.autograd.grad(y, [x, b], dy, create_graph=True)
+    assert_close(db, dx.detach().float().sum([0, 2, 3]).cpu(), 1e-2 if dtype == torch.float16 else 2e-5, 'db = sum dx')
+    v, u = torch.randn_like(dx), torch.randn_like(db)
+    d_dy, = torch.autograd.grad([dx, db], dy, [v, u])
+    yd = y.detach().float()
+    slope = torch.where(yd > 0, torch.full_like(yd, float(np.sqrt(2))), torch.full_like(yd, float(np.sqrt(2)) * 0.2)) * (yd.abs() < 1.5)
+    ref = slope * (v.float() + u.float().reshape(1, -1, 1, 1))
+    assert_close(d_dy, ref.cpu(), 1e-2 if dtype == torch.float16 else 2e-5, 'd_dy')
+    only_db, = torch.autograd.grad(torch.autograd.grad(y, [b], dy, create_graph=True)[0], dy, u)
+    assert_close(only_db, (slope * u.float().reshape(1, -1, 1, 1)).cpu(), 1e-2 if dtype == torch.float16 else 2e-5, 'd_dy from db alone')
+
+
 def test_bias_act_linear_clamp_grad():
     """Reference CUDA semantics: `linear` saves no output, so the clamp does not mask its gradient (OPS/bias_act.py:151-154)."""
     x = (torch.randn(2, 3, 4, 4, device=DEV) * 300).requires_grad_(True)
