@@ -31,7 +31,15 @@ int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long lon
                          long long ss_w, int SH, int SW, int SC, int N, int stride, int pad, float* workspace, long long workspace_floats,
                          cudaStream_t stream);
 void gt_wgrad_halo_enable_s2(int on);
-static int g_wgrad_variant = 0;   // 0 = auto (halo kernel where it applies), 1 = per-tap-row kernel only, 2 = halo kernel for stride 1 only
+// conv_wgrad_halo_wide.cu: N = 128 U channels per CTA, kernel rows split over two CTA types (stride-1 3x3 layers with UC % 128 == 0)
+bool gt_wgrad_halo_wide_applicable(int N, int UH, int UW, int UC, int SC, int SH, int SW, int KH, int KW, int stride, int pad);
+long long gt_wgrad_halo_wide_workspace(int N, int UH, int UW, int UC, int SC);
+int gt_launch_wgrad_halo_wide(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n,
+                              long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int pad, float* workspace, long long workspace_floats, int* nA,
+                              int* nB, cudaStream_t stream);
+void gt_wgrad_halo_wide_enable(int on);
+static int g_wgrad_variant = 0;   // 0 = auto (halo kernels where they apply), 1 = per-tap-row kernel only, 2 = halo kernel for stride 1 only,
+                                  // 3 = no wide (N = 128) halo kernel
 // > 0: at most this many pixels per split-K slice.  Set (per calling thread) around the fp16x3 entry points: the tensor core's truncating
 // accumulation must stay below ~100 main-term updates per accumulator for fp32 accuracy (csrc/conv_f16x3.cu).
 thread_local int t_wgrad_px_limit = 0;
@@ -39,6 +47,7 @@ extern "C" int gt_conv_wgrad_config(int variant) {
     const int old = g_wgrad_variant;
     g_wgrad_variant = variant;
     gt_wgrad_halo_enable_s2(variant != 2);
+    gt_wgrad_halo_wide_enable(variant != 3);
     return old;
 }
 
@@ -228,6 +237,35 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
+// 3x3 result of conv_wgrad_halo_wide.cu: taps 0..5 from region A ([nA][6][UC][SC]), taps 6..8 from region B ([nB][3][UC][SC]), each summed in
+// slice order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_ab_kernel(const float* __restrict__ wsA, int nA, const float* __restrict__ wsB, int nB, int UC, int SC,
+                                                              const WgradOut o) {
+    const uint32_t pairs = (uint32_t)UC * (uint32_t)SC;
+    const uint32_t total = 9u * pairs;
+    const float inv = o.f32 ? (1.f / gt_scale_from_amax_bits(*o.amax_u)) * (1.f / gt_scale_from_amax_bits(*o.amax_s)) : 1.f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t tap = i / pairs, pr = i - tap * pairs;
+        const uint32_t u = pr / (uint32_t)SC, s = pr - u * (uint32_t)SC;
+        if ((int)u >= o.UCr || (int)s >= o.SCr) continue;
+        const bool a = tap < 6;
+        const float* p = a ? wsA + (size_t)tap * pairs + pr : wsB + (size_t)(tap - 6) * pairs + pr;
+        const size_t per = (size_t)(a ? 6 : 3) * pairs;
+        const int splits = a ? nA : nB;
+        float acc = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4) {
+            const float a0 = p[(size_t)sp * per], a1 = p[(size_t)(sp + 1) * per], a2 = p[(size_t)(sp + 2) * per], a3 = p[(size_t)(sp + 3) * per];
+            acc = (((acc + a0) + a1) + a2) + a3;
+        }
+        for (; sp < splits; sp++) acc += p[(size_t)sp * per];
+        const int r = (int)tap / 3, c = (int)tap - r * 3;
+        const long long off = (long long)u * o.ds_u + (long long)s * o.ds_s + r * o.ds_r + c * o.ds_c;
+        if (o.f32) ((float*)o.dw)[off] = acc * inv;
+        else ((__half*)o.dw)[off] = __float2half_rn(acc);
+    }
+}
+
 int next_pow2_log2(int v) {
     int l = 0;
     while ((1 << l) < v) l++;
@@ -306,6 +344,10 @@ static long long wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, 
             const long long h = gt_wgrad_halo_workspace(N, UH, UW, UC, SC, stride);
             if (h > need) need = h;
         }
+        if (UC % 128 == 0) {
+            const long long h = gt_wgrad_halo_wide_workspace(N, UH, UW, UC, SC);
+            if (h > need) need = h;
+        }
     }
     return need;
 }
@@ -324,6 +366,17 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
     GT_REQUIRE(us_w % 8 == 0 && us_h % 8 == 0 && us_n % 8 == 0 && ss_w % 8 == 0 && ss_h % 8 == 0 && ss_n % 8 == 0,
                "gt_conv2d_wgrad_f16: strides must be multiples of 8 elements");
     const int ntaps = KH * KW;
+    if (g_wgrad_variant != 1 && gt_wgrad_halo_wide_applicable(N, UH, UW, UC, SC, SH, SW, KH, KW, stride, pad)) {
+        int nA = 0, nB = 0;
+        if (gt_launch_wgrad_halo_wide(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, pad, workspace, workspace_floats, &nA, &nB,
+                                      (cudaStream_t)stream) != 0)
+            return GT_ERR_CUDA;
+        long long g = ((long long)ntaps * UC * SC + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        wgrad_reduce_ab_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, nA, workspace + (long long)nA * 6 * UC * SC, nB, UC, SC, wo);
+        GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
+        return GT_OK;
+    }
     if (g_wgrad_variant != 1 && gt_wgrad_halo_applicable(N, UH, UW, UC, SC, SH, SW, KH, KW, stride, pad)) {
         const int splits = gt_launch_wgrad_halo(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, stride, pad, workspace, workspace_floats,
                                                 (cudaStream_t)stream);

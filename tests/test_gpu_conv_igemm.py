@@ -37,6 +37,11 @@ CASES = [
     ('3x3_s2_128_64_66x90_n5', 5, 128, 64, 66, 90, 3, 2, 0, False),
     ('3x3_T_s2_128_64_36x44_n3', 3, 128, 64, 36, 44, 3, 2, 0, True),
     ('3x3_T_s2_256_128_32_n4', 4, 256, 128, 32, 32, 3, 2, 0, True),
+    # stride-1 3x3 with >= 128 U channels and enough pixel tiles per CTA for the wide (N = 128, two CTA types) weight-gradient kernel
+    # (csrc/conv_wgrad_halo_wide.cu), incl. ragged tiles and the transposed form (U = x)
+    ('3x3_p1_128_128_96_n8', 8, 128, 128, 96, 96, 3, 1, 1, False),
+    ('3x3_p1_256_128_40x72_n8', 8, 256, 128, 40, 72, 3, 1, 1, False),
+    ('3x3_T_s1_p1_128_256_56_n8', 8, 128, 256, 56, 56, 3, 1, 1, True),
 ]
 
 
