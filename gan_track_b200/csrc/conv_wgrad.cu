@@ -33,10 +33,10 @@ int gt_launch_wgrad_halo(const void* u, long long us_n, long long us_h, long lon
 void gt_wgrad_halo_enable_s2(int on);
 // conv_wgrad_halo_wide.cu: N = 128 U channels per CTA, kernel rows split over two CTA types (stride-1 3x3 layers with UC % 128 == 0)
 bool gt_wgrad_halo_wide_applicable(int N, int UH, int UW, int UC, int SC, int SH, int SW, int KH, int KW, int stride, int pad);
-long long gt_wgrad_halo_wide_workspace(int N, int UH, int UW, int UC, int SC);
+long long gt_wgrad_halo_wide_workspace(int N, int UH, int UW, int UC, int SC, int stride);
 int gt_launch_wgrad_halo_wide(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s, long long ss_n,
-                              long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int pad, float* workspace, long long workspace_floats, int* nA,
-                              int* nB, cudaStream_t stream);
+                              long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int stride, int pad, float* workspace,
+                              long long workspace_floats, int* nA, int* nB, int* pos_of, cudaStream_t stream);
 void gt_wgrad_halo_wide_enable(int on);
 static int g_wgrad_variant = 0;   // 0 = auto (halo kernels where they apply), 1 = per-tap-row kernel only, 2 = halo kernel for stride 1 only,
                                   // 3 = no wide (N = 128) halo kernel
@@ -237,10 +237,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
-// 3x3 result of conv_wgrad_halo_wide.cu: taps 0..5 from region A ([nA][6][UC][SC]), taps 6..8 from region B ([nB][3][UC][SC]), each summed in
-// slice order (deterministic)
+// 3x3 result of conv_wgrad_halo_wide.cu: tap positions 0..5 from region A ([nA][6][UC][SC]), 6..8 from region B ([nB][3][UC][SC]), each summed in
+// slice order (deterministic); pos.p[tap] = position of tap r * 3 + s
+struct TapPos {
+    int p[9];
+};
 __global__ void __launch_bounds__(256) wgrad_reduce_ab_kernel(const float* __restrict__ wsA, int nA, const float* __restrict__ wsB, int nB, int UC, int SC,
-                                                              const WgradOut o) {
+                                                              const TapPos pos, const WgradOut o) {
     const uint32_t pairs = (uint32_t)UC * (uint32_t)SC;
     const uint32_t total = 9u * pairs;
     const float inv = o.f32 ? (1.f / gt_scale_from_amax_bits(*o.amax_u)) * (1.f / gt_scale_from_amax_bits(*o.amax_s)) : 1.f;
@@ -248,8 +251,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_ab_kernel(const float* __res
         const uint32_t tap = i / pairs, pr = i - tap * pairs;
         const uint32_t u = pr / (uint32_t)SC, s = pr - u * (uint32_t)SC;
         if ((int)u >= o.UCr || (int)s >= o.SCr) continue;
-        const bool a = tap < 6;
-        const float* p = a ? wsA + (size_t)tap * pairs + pr : wsB + (size_t)(tap - 6) * pairs + pr;
+        const int ps = pos.p[tap];
+        const bool a = ps < 6;
+        const float* p = a ? wsA + (size_t)ps * pairs + pr : wsB + (size_t)(ps - 6) * pairs + pr;
         const size_t per = (size_t)(a ? 6 : 3) * pairs;
         const int splits = a ? nA : nB;
         float acc = 0.f;
@@ -345,8 +349,10 @@ static long long wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, 
             if (h > need) need = h;
         }
         if (UC % 128 == 0) {
-            const long long h = gt_wgrad_halo_wide_workspace(N, UH, UW, UC, SC);
-            if (h > need) need = h;
+            for (int stride = 1; stride <= 2; stride++) {
+                const long long h = gt_wgrad_halo_wide_workspace(N, UH, UW, UC, SC, stride);
+                if (h > need) need = h;
+            }
         }
     }
     return need;
@@ -368,12 +374,13 @@ static int wgrad_impl(const void* u, long long us_n, long long us_h, long long u
     const int ntaps = KH * KW;
     if (g_wgrad_variant != 1 && gt_wgrad_halo_wide_applicable(N, UH, UW, UC, SC, SH, SW, KH, KW, stride, pad)) {
         int nA = 0, nB = 0;
-        if (gt_launch_wgrad_halo_wide(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, pad, workspace, workspace_floats, &nA, &nB,
-                                      (cudaStream_t)stream) != 0)
+        TapPos pos;
+        if (gt_launch_wgrad_halo_wide(u, us_n, us_h, us_w, UH, UW, UC, s, ss_n, ss_h, ss_w, SH, SW, SC, N, stride, pad, workspace, workspace_floats, &nA, &nB,
+                                      pos.p, (cudaStream_t)stream) != 0)
             return GT_ERR_CUDA;
         long long g = ((long long)ntaps * UC * SC + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
-        wgrad_reduce_ab_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, nA, workspace + (long long)nA * 6 * UC * SC, nB, UC, SC, wo);
+        wgrad_reduce_ab_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(workspace, nA, workspace + (long long)nA * 6 * UC * SC, nB, UC, SC, pos, wo);
         GT_CUDA_LAUNCH_CHECK("gt_conv2d_wgrad_f16 (reduce)");
         return GT_OK;
     }

@@ -42,6 +42,9 @@ CASES = [
     ('3x3_p1_128_128_96_n8', 8, 128, 128, 96, 96, 3, 1, 1, False),
     ('3x3_p1_256_128_40x72_n8', 8, 256, 128, 40, 72, 3, 1, 1, False),
     ('3x3_T_s1_p1_128_256_56_n8', 8, 128, 256, 56, 56, 3, 1, 1, True),
+    # ... and its stride-2 (parity-plane) form
+    ('3x3_s2_256_512_33_n24', 24, 256, 512, 33, 33, 3, 2, 0, False),
+    ('3x3_T_s2_512_256_16_n24', 24, 512, 256, 16, 16, 3, 2, 0, True),
 ]
 
 
