@@ -46,10 +46,53 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
         const float t = steps[ch.seg];
         const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
         const float step_size = lr / bc1, rsq_bc2 = 1.f / sqrtf(bc2);
-        for (int i = threadIdx.x; i < ch.count; i += 256) {
+        // parameters / moments start on 16-byte boundaries (FlatParams aligns every parameter to 64 floats, chunks are multiples of 4 long
+        // except a parameter's last one): 16-byte accesses for p, m, v; the compact gradient buffer has no such alignment -> scalar accesses
+        const int n4 = ((ch.pstart & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(m) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(v) & 15) == 0)
+                           ? (ch.count >> 2)
+                           : 0;
+        float4* p4 = reinterpret_cast<float4*>(p + ch.pstart);
+        float4* m4 = reinterpret_cast<float4*>(m + ch.pstart);
+        float4* v4 = reinterpret_cast<float4*>(v + ch.pstart);
+        float* gp = grad + ch.gstart;
+        const bool g_aligned = ((ch.gstart & 3) == 0) && ((reinterpret_cast<uintptr_t>(grad) & 15) == 0);
+        for (int i = threadIdx.x; i < n4; i += 256) {
+            float4 pp = p4[i], mm = m4[i], vv = v4[i];
+            float g[4];
+            if (g_aligned) {
+                const float4 gv = reinterpret_cast<const float4*>(gp)[i];
+                g[0] = scrub(gv.x, grad_scale, posinf, neginf);
+                g[1] = scrub(gv.y, grad_scale, posinf, neginf);
+                g[2] = scrub(gv.z, grad_scale, posinf, neginf);
+                g[3] = scrub(gv.w, grad_scale, posinf, neginf);
+                reinterpret_cast<float4*>(gp)[i] = make_float4(g[0], g[1], g[2], g[3]);   // the reduced, scrubbed gradient stays readable (tests, stats)
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) g[k] = scrub(gp[4 * i + k], grad_scale, posinf, neginf);
+#pragma unroll
+                for (int k = 0; k < 4; k++) gp[4 * i + k] = g[k];
+            }
+            float* pe = reinterpret_cast<float*>(&pp);
+            float* me = reinterpret_cast<float*>(&mm);
+            float* ve = reinterpret_cast<float*>(&vv);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float m1 = me[k] + (g[k] - me[k]) * (1.f - b1);
+                const float v1 = ve[k] * b2 + g[k] * g[k] * (1.f - b2);
+                me[k] = m1;
+                ve[k] = v1;
+                const float denom = sqrtf(v1) * rsq_bc2 + eps;
+                pe[k] = pe[k] - step_size * (m1 / denom);
+            }
+            m4[i] = mm;
+            v4[i] = vv;
+            p4[i] = pp;
+        }
+        for (int i = 4 * n4 + threadIdx.x; i < ch.count; i += 256) {
             const long long e = ch.pstart + i, ge = ch.gstart + i;
             const float g = scrub(grad[ge], grad_scale, posinf, neginf);
-            grad[ge] = g;                                   // the reduced, scrubbed gradient stays readable (tests, stats)
+            grad[ge] = g;
             const float mm = m[e] + (g - m[e]) * (1.f - b1);
             const float vv = v[e] * b2 + g * g * (1.f - b2);
             m[e] = mm;
