@@ -274,7 +274,8 @@ def hot_kernel_rooflines(device, pk):
         ms = timeit([lambda x=x: conv_igemm.igemm_forward(x, w, transpose=False, packed=pkd, **cfg) for x in xs])
         add(f'conv_igemm_halo fwd 3x3 {ci}->{co} @{r}x{r}', tag, 'tensor', fl, ms)
         ms = timeit([lambda x=x: conv_igemm.igemm_wgrad(x, x, (co, ci, 3, 3), transpose=False, **cfg) for x in xs])
-        add(f'conv_wgrad_halo 3x3 {ci}x{co} over 32x{r}x{r} pixels', 'conv_wgrad_halo_kernel<1> + wgrad_reduce_kernel', 'tensor', fl, ms)
+        add(f'conv_wgrad_halo 3x3 {ci}x{co} over 32x{r}x{r} pixels',
+            'conv_wgrad_halo_wide_kernel<1> + wgrad_reduce_ab_kernel' if co % 128 == 0 else 'conv_wgrad_halo_kernel<1> + wgrad_reduce_kernel', 'tensor', fl, ms)
         del xs
 
     f = upfirdn2d.setup_filter([1, 3, 3, 1], device=device)
