@@ -18,15 +18,18 @@
 // Per step: one 16.6 KB TMA row load (contiguous in global memory), 12-13 MMAs (~1170 clk), one 16 KB TMA row store -- every input
 // byte is fetched once per strip (+ 2 halo pixels per row), the weights (72 KB) stay in shared memory for the whole persistent CTA.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> [bias_act] -> fp16
-// -> swizzled shared memory -> TMA store).  Work split: the N * strips * H output rows are cut into contiguous ranges, one per CTA.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue (TMEM -> registers -> [bias_act] -> fp16 -> swizzled shared
+// memory -> TMA store): four warps for the plain store; EIGHT with the fused bias_act (two per TMEM lane quarter, each taking 32 of the 64
+// output channels, the bias in registers) -- with four, one warp per scheduler has nothing to hide the dependent conversion / activation
+// chains behind and the kernel becomes epilogue-paced (measured: 282 us fused against 103 us for the plain kernel).  Work split: the N * strips * H output rows are cut into contiguous ranges, one per CTA.
 #include "conv_common.cuh"
 
 using namespace sm100;
 
 namespace {
 
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;                             // plain store: producer + issuer + 4 epilogue warps
+constexpr int NTHREADS_EP = 320;                          // fused bias_act: 8 epilogue warps (two per TMEM lane quarter, 32 of the 64 columns each)
 constexpr int STRIP = 128;                                // output pixels per step = UMMA M
 constexpr int ROW_PX = STRIP + 2;                         // + one halo pixel each side
 constexpr uint32_t ROW_BYTES = ROW_PX * 128;              // 16640: 130 pixels x 64 channels fp16
@@ -73,8 +76,18 @@ __device__ __forceinline__ Seg segment_at(const RowsParams& p, long long row, lo
     return s;
 }
 
+template <int ACT, bool CLAMP>
+__device__ __forceinline__ void ep_apply(__half2 (&h)[4], const __half2* bias4, bool has_bias, const hot::Params& hp) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float2 u = __half22float2(h[k]);                    // round to fp16 first: the reference materialises the convolution output
+        if (has_bias) u = __fadd2_rn(u, __half22float2(bias4[k]));
+        h[k] = __float22half2_rn(hot::fwd<ACT, CLAMP>(u, hp));
+    }
+}
+
 template <bool EP>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(EP ? NTHREADS_EP : NTHREADS, 1) conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmY, const RowsParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_rows_kernel(const __grid_con
         }
         for (int i = 0; i < NBLK; i++) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);          // one arrival per epilogue warp
+            mbar_init(&acc_empty[i], EP ? 8 : 4);          // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -204,7 +217,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_rows_kernel(const __grid_con
         const int q = warp & 3;
         const int m = q * 32 + lane;                                     // pixel of the strip = TMEM lane
         const bool issuer = (warp == 2 && lane == 0);
+        constexpr int EP_THREADS = EP ? 256 : 128;
+        const int half = EP ? ((warp - 2) >> 2) : 0;                     // fused epilogue: which 32 of the 64 output channels this warp takes
         const hot::Params hp = hot::make_params(p.ep_alpha, p.ep_gain, p.ep_clamp);
+        const bool has_bias = EP && p.ep_bias != nullptr;
+        const int ep_mode = EP ? ((p.ep_act == hot::LRELU ? 2 : 0) + (p.ep_clamp >= 0.f ? 1 : 0)) : 0;
+        __half2 bias_r[16];                                              // the warp's 32 bias values
+        if (EP) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                Vec16<__half> bv;
+                if (has_bias) bv = ld16(p.ep_bias + half * 32 + g * 8);
+#pragma unroll
+                for (int k = 0; k < 4; k++) bias_r[g * 4 + k] = has_bias ? reinterpret_cast<const __half2*>(bv.v)[k] : __floats2half2_rn(0.f, 0.f);
+            }
+        }
         uint32_t j = 0, nstore = 0;
         for (long long row = row_begin; row < row_end;) {
             const Seg s = segment_at(p, row, row_end);
@@ -217,10 +244,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_rows_kernel(const __grid_con
                 if (valid) {
                     uint8_t* stage = sStage + (nstore % NSTAGE) * STAGE_BYTES;
                     if (issuer) bulk_wait_read<NSTAGE - 1>();            // the store that last read this staging buffer has drained it
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, EP_THREADS);
                     const uint32_t srow = smem_u32(stage) + (uint32_t)m * 128u;
 #pragma unroll
-                    for (int c = 0; c < 2; c++) {
+                    for (int cc = 0; cc < (EP ? 1 : 2); cc++) {
+                        const int c = EP ? half : cc;
                         uint32_t v[32];
                         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b0 * 64 + (uint32_t)(c * 32), v);
                         tmem_ld_wait();
@@ -230,20 +258,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_rows_kernel(const __grid_con
 #pragma unroll
                             for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
                             if (EP) {
-                                // round to fp16 first (the reference materialises the convolution output before bias_act reads it back)
-                                const int co0 = c * 32 + g * 8;
-                                Vec16<__half> bv;
-                                if (p.ep_bias) bv = ld16(p.ep_bias + co0);
-                                const bool clamp_on = p.ep_clamp >= 0.f;
-#pragma unroll
-                                for (int k = 0; k < 4; k++) {
-                                    float2 u = __half22float2(h[k]);
-                                    if (p.ep_bias) u = __fadd2_rn(u, __half22float2(reinterpret_cast<const __half2*>(bv.v)[k]));
-                                    float2 o;
-                                    if (p.ep_act == hot::LRELU) o = clamp_on ? hot::fwd<hot::LRELU, true>(u, hp) : hot::fwd<hot::LRELU, false>(u, hp);
-                                    else o = clamp_on ? hot::fwd<hot::LINEAR, true>(u, hp) : hot::fwd<hot::LINEAR, false>(u, hp);
-                                    h[k] = __float22half2_rn(o);
-                                }
+                                if (ep_mode == 3) ep_apply<hot::LRELU, true>(h, bias_r + g * 4, has_bias, hp);
+                                else if (ep_mode == 2) ep_apply<hot::LRELU, false>(h, bias_r + g * 4, has_bias, hp);
+                                else if (ep_mode == 1) ep_apply<hot::LINEAR, true>(h, bias_r + g * 4, has_bias, hp);
+                                else ep_apply<hot::LINEAR, false>(h, bias_r + g * 4, has_bias, hp);
                             }
                             uint4 o4;
                             o4.x = *reinterpret_cast<uint32_t*>(&h[0]);
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_rows_kernel(const __grid_con
                     }
                     tc_fence_before();
                     fence_proxy_async();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, EP_THREADS);
                     if (issuer) {
                         tma_store_4d(stage, &tmY, 0, s.x0, y, s.n);      // pixels past the image width are clipped by the TMA unit
                         bulk_commit();
@@ -367,7 +385,7 @@ int gt_launch_conv_rows(const void* x, long long xs_n, long long xs_h, long long
         }
         configured[ep] = true;
     }
-    if (ep) conv_rows_kernel<true><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(tmA, tmB, tmY, rp);
+    if (ep) conv_rows_kernel<true><<<grid, NTHREADS_EP, SMEM_TOTAL, stream>>>(tmA, tmB, tmY, rp);
     else conv_rows_kernel<false><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(tmA, tmB, tmY, rp);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm_f16 (rows)");
     return GT_OK;

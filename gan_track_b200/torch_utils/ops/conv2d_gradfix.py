@@ -134,10 +134,23 @@ def _empty(like):
 
 _ACT_CODE = {'linear': 1, 'lrelu': 3}
 import os as _os
-# Measured on B200 (A/B in one session, batch 32, 256x256): with the epilogue fused the step is 58.3 ms, without 56.6 ms -- the
-# narrow (64/128-channel) layers are epilogue-paced, so the extra per-element work in the TMEM -> global path costs more than
-# the saved bias_act pass.  OFF by default; GT_FUSE_BIAS_ACT=1 (or the attribute) switches it on.  Both forms are tested.
-fuse_bias_act = _os.environ.get('GT_FUSE_BIAS_ACT', '0') == '1'
+# True: fuse wherever the tcgen05 kernels take the convolution; False: never; 'auto' (default): where it was measured to win on B200
+# (tools/bench_fused_epilogue.py, profiles/r02_fused_epilogue.txt; us per layer forward at batch 32, separate -> fused):
+#   64 -> 64 3x3 @256^2 (row-streaming kernel, eight epilogue warps)   see the profile      1x1 skips                 111 -> 83
+#   3x3 stride 1, >= 256 output channels                     131 -> 120, 130 -> 122         512 -> 512 stride 2 @33     98 -> 68
+# and NOT on the 128-channel stride-1 layers (158 -> 167) or the other stride-2 layers (121 -> 140, 99 -> 112): those kernels have four
+# epilogue warps and become epilogue-paced with the extra per-element work.  GT_FUSE_BIAS_ACT=0 / 1 / auto (or the attribute).
+_env = _os.environ.get('GT_FUSE_BIAS_ACT', 'auto')
+fuse_bias_act = True if _env == '1' else (False if _env == '0' else 'auto')
+
+
+def _fuse_profitable(input, weight, stride):
+    cout, cin, kh, kw = weight.shape
+    if kh == 1 and kw == 1:
+        return True
+    if stride == (1, 1):
+        return (cin == 64 and cout == 64 and input.shape[3] >= 128) or cout >= 256
+    return cin >= 512
 
 
 def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, clamp=None, stride=1, padding=0):
@@ -149,7 +162,8 @@ def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, cl
     from . import bias_act as bias_act_mod
     from . import conv_igemm
     stride, padding = _pair(stride), _pair(padding)
-    fusable = (fuse_bias_act and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
+    fusable = (fuse_bias_act is not False and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
+               and (fuse_bias_act is True or _fuse_profitable(input, weight, stride))
                and conv_igemm.covered(input, weight, False, (0, 0), stride, padding, 1) and (bias is None or bias.numel() % 8 == 0))
     if not fusable:
         y = conv2d(input, weight, stride=stride, padding=padding)

@@ -187,7 +187,8 @@ def test_fp32_conv_f16x3_accuracy(case, scale):
 
 
 @pytest.mark.parametrize('act,gain,clamp,bias', [('lrelu', None, 256.0, True), ('lrelu', 0.7, 0.5, True), ('linear', 0.7071, 181.0, True), ('linear', None, None, False)])
-@pytest.mark.parametrize('shape', [(4, 64, 64, 40, 40, 3, 1, 1), (3, 128, 256, 33, 33, 3, 2, 0), (2, 128, 64, 16, 16, 1, 1, 0)])
+@pytest.mark.parametrize('shape', [(4, 64, 64, 40, 40, 3, 1, 1), (3, 128, 256, 33, 33, 3, 2, 0), (2, 128, 64, 16, 16, 1, 1, 0),
+                                   (2, 64, 64, 70, 200, 3, 1, 1), (1, 64, 64, 129, 257, 3, 1, 1)])        # row-streaming kernel, eight epilogue warps
 def test_conv_bias_act_fused_epilogue_equals_unfused(shape, act, gain, clamp, bias):
     """bias_act fused into the convolution's epilogue (csrc/conv_common.cuh: conv_store32) against convolution followed by the
     bias_act kernel: identical values (same rounding points), identical first-order gradients, and the R1-style second order."""
