@@ -21,6 +21,8 @@ using namespace sm100;
 namespace {
 
 constexpr int NTHREADS = 192;
+constexpr int NTHREADS_EP = 320;     // fused bias_act: eight epilogue warps (two per TMEM lane quarter, alternating 32-column chunks); with four the
+                                     // extra per-element work makes the narrow layers epilogue-paced (128 channels: 158 us separate, 167 us fused)
 constexpr int SUB_W = 8, SUB_H = 16;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // shared::cluster address -> same offset in the pair's even (leader) CTA
 
@@ -101,7 +103,7 @@ __device__ __forceinline__ Item2 decode_item2(const ConvParams& p, int item, int
 }
 
 template <int BN, int MT, int SB, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == CONV_F16_EP ? NTHREADS_EP : NTHREADS, 1)
     conv_igemm_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p, const int total_items) {
     typedef Halo2Smem<BN, MT, SB> L;
     constexpr int CTA_W = SUB_W * MT, PAIR_W = 2 * CTA_W;     // pixels per CTA / per pair along x
@@ -133,7 +135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             mbar_init(&a_full[i], 1);       // leader's producer arrive + both CTAs' bytes
             mbar_init(&a_empty[i], 1);      // one multicast commit
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 8);      // four epilogue warps of each CTA (only the leader's is waited on)
+            mbar_init(&t_empty[i], MODE == CONV_F16_EP ? 16 : 8);      // the epilogue warps of both CTAs (only the leader's is waited on)
         }
         for (int i = 0; i < SB; i++) {
             mbar_init(&b_full[i], 1);
@@ -223,6 +225,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int lw = m & (SUB_W - 1), lh = m >> 3;
+        constexpr int CSETS = MODE == CONV_F16_EP ? 2 : 1;            // warp sets sharing a lane quarter take alternating column chunks
+        const int cset = MODE == CONV_F16_EP ? ((warp - 2) >> 2) : 0;
         uint32_t t_it = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const Item2 it = decode_item2(p, item, PAIR_W);
@@ -239,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                 const long long yoff = (long long)it.n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
                                        (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = cset; c < BN / 32; c += CSETS) {
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c * 32), r);
                     tmem_ld_wait();
@@ -275,7 +279,7 @@ int launch_halo2_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPar
     }
     int clusters = gt_num_sms() / 2;
     if (clusters > total_items) clusters = total_items;
-    conv_igemm_halo2_kernel<BN, MT, SB, MODE><<<2 * clusters, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
+    conv_igemm_halo2_kernel<BN, MT, SB, MODE><<<2 * clusters, MODE == CONV_F16_EP ? NTHREADS_EP : NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm (halo, CTA pair)");
     return GT_OK;
 }

@@ -76,13 +76,31 @@ __device__ __forceinline__ Seg segment_at(const RowsParams& p, long long row, lo
     return s;
 }
 
-template <int ACT, bool CLAMP>
-__device__ __forceinline__ void ep_apply(__half2 (&h)[4], const __half2* bias4, bool has_bias, const hot::Params& hp) {
+
+// 32 accumulator columns of one pixel -> [bias_act] -> fp16 -> four swizzled 16-byte chunks of the pixel's staged 128-byte row.  One
+// straight-line instantiation per (activation, clamp): 16 independent half2 chains for the scheduler to interleave.
+template <bool EP, int ACT, bool CLAMP>
+__device__ __forceinline__ void stage_cols(const uint32_t (&v)[32], const __half2 (&bias_r)[16], bool has_bias, const hot::Params& hp, uint32_t srow, int c,
+                                           int m) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float2 u = __half22float2(h[k]);                    // round to fp16 first: the reference materialises the convolution output
-        if (has_bias) u = __fadd2_rn(u, __half22float2(bias4[k]));
-        h[k] = __float22half2_rn(hot::fwd<ACT, CLAMP>(u, hp));
+    for (int g = 0; g < 4; g++) {
+        __half2 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h[k] = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
+            if (EP) {
+                float2 u = __half22float2(h[k]);                    // round to fp16 first: the reference materialises the convolution output
+                if (has_bias) u = __fadd2_rn(u, __half22float2(bias_r[g * 4 + k]));
+                h[k] = __float22half2_rn(hot::fwd<ACT, CLAMP>(u, hp));
+            }
+        }
+        uint4 o4;
+        o4.x = *reinterpret_cast<uint32_t*>(&h[0]);
+        o4.y = *reinterpret_cast<uint32_t*>(&h[1]);
+        o4.z = *reinterpret_cast<uint32_t*>(&h[2]);
+        o4.w = *reinterpret_cast<uint32_t*>(&h[3]);
+        const uint32_t chunk = (uint32_t)(c * 4 + g);                           // 16-byte chunk of the pixel's 128-byte row
+        sts128(srow + ((chunk ^ ((uint32_t)m & 7u)) << 4), o4);                 // SWIZZLE_128B: chunk ^ (row mod 8)
     }
 }
 
@@ -252,25 +270,11 @@ __global__ void __launch_bounds__(EP ? NTHREADS_EP : NTHREADS, 1) conv_rows_kern
                         uint32_t v[32];
                         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + b0 * 64 + (uint32_t)(c * 32), v);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            __half2 h[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
-                            if (EP) {
-                                if (ep_mode == 3) ep_apply<hot::LRELU, true>(h, bias_r + g * 4, has_bias, hp);
-                                else if (ep_mode == 2) ep_apply<hot::LRELU, false>(h, bias_r + g * 4, has_bias, hp);
-                                else if (ep_mode == 1) ep_apply<hot::LINEAR, true>(h, bias_r + g * 4, has_bias, hp);
-                                else ep_apply<hot::LINEAR, false>(h, bias_r + g * 4, has_bias, hp);
-                            }
-                            uint4 o4;
-                            o4.x = *reinterpret_cast<uint32_t*>(&h[0]);
-                            o4.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                            o4.z = *reinterpret_cast<uint32_t*>(&h[2]);
-                            o4.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                            const uint32_t chunk = (uint32_t)(c * 4 + g);                           // 16-byte chunk of the pixel's 128-byte row
-                            sts128(srow + ((chunk ^ ((uint32_t)m & 7u)) << 4), o4);                 // SWIZZLE_128B: chunk ^ (row mod 8)
-                        }
+                        if (!EP) stage_cols<false, hot::LINEAR, false>(v, bias_r, false, hp, srow, c, m);
+                        else if (ep_mode == 3) stage_cols<true, hot::LRELU, true>(v, bias_r, has_bias, hp, srow, c, m);
+                        else if (ep_mode == 2) stage_cols<true, hot::LRELU, false>(v, bias_r, has_bias, hp, srow, c, m);
+                        else if (ep_mode == 1) stage_cols<true, hot::LINEAR, true>(v, bias_r, has_bias, hp, srow, c, m);
+                        else stage_cols<true, hot::LINEAR, false>(v, bias_r, has_bias, hp, srow, c, m);
                     }
                     tc_fence_before();
                     fence_proxy_async();

@@ -135,22 +135,21 @@ def _empty(like):
 _ACT_CODE = {'linear': 1, 'lrelu': 3}
 import os as _os
 # True: fuse wherever the tcgen05 kernels take the convolution; False: never; 'auto' (default): where it was measured to win on B200
-# (tools/bench_fused_epilogue.py, profiles/r02_fused_epilogue.txt; us per layer forward at batch 32, separate -> fused):
-#   64 -> 64 3x3 @256^2 (row-streaming kernel, eight epilogue warps)   see the profile      1x1 skips                 111 -> 83
-#   3x3 stride 1, >= 256 output channels                     131 -> 120, 130 -> 122         512 -> 512 stride 2 @33     98 -> 68
-# and NOT on the 128-channel stride-1 layers (158 -> 167) or the other stride-2 layers (121 -> 140, 99 -> 112): those kernels have four
-# epilogue warps and become epilogue-paced with the extra per-element work.  GT_FUSE_BIAS_ACT=0 / 1 / auto (or the attribute).
+# (tools/bench_fused_epilogue.py -> profiles/r02_fused_epilogue.txt; us per layer forward at batch 32, separate -> fused):
+#   64 -> 64 3x3 @256^2 (row-streaming kernel)  205 -> 139      128 -> 128 3x3 @128^2  159 -> 133      256 -> 256 3x3 @64^2  133 -> 116
+#   512 -> 512 3x3 @32^2  132 -> 123            1x1 skip 64 -> 128 @128^2  112 -> 83          64 -> 128 stride 2 @257  182 -> 174
+# and NOT on the stride-2 layers with 128 / 256 input channels (122 -> 141, 103 -> 111: the per-tap kernel's epilogue is not overlapped
+# with the next tile's MMAs).  The fused mode of the row-streaming and CTA-pair kernels runs EIGHT epilogue warps: with four, the extra
+# per-element work made the narrow layers epilogue-paced (64 channels: 282 us fused).  GT_FUSE_BIAS_ACT=0 / 1 / auto (or the attribute).
 _env = _os.environ.get('GT_FUSE_BIAS_ACT', 'auto')
 fuse_bias_act = True if _env == '1' else (False if _env == '0' else 'auto')
 
 
 def _fuse_profitable(input, weight, stride):
     cout, cin, kh, kw = weight.shape
-    if kh == 1 and kw == 1:
-        return True
     if stride == (1, 1):
-        return (cin == 64 and cout == 64 and input.shape[3] >= 128) or cout >= 256
-    return cin >= 512
+        return True
+    return cin <= 64 or cin >= 512
 
 
 def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, clamp=None, stride=1, padding=0):
