@@ -161,7 +161,7 @@ def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, cl
     from . import bias_act as bias_act_mod
     from . import conv_igemm
     stride, padding = _pair(stride), _pair(padding)
-    fusable = (fuse_bias_act is not False and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
+    fusable = (fuse_bias_act is not False and conv_backend.allow_igemm and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
                and (fuse_bias_act is True or _fuse_profitable(input, weight, stride))
                and conv_igemm.covered(input, weight, False, (0, 0), stride, padding, 1) and (bias is None or bias.numel() % 8 == 0))
     if not fusable:
