@@ -72,6 +72,7 @@ _PROTOTYPES = {
     'gt_conv2d_wgrad_f16x3_workspace': (_ll, [_i, _i, _i, _i, _i, _i, _i]),
     'gt_conv2d_wgrad_f16x3': (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp]),
     'gt_conv2d_igemm_f16_bias_act': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp]),
+    'gt_conv2d_igemm_f16_bias_act_add': (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _vp]),
     'gt_conv2d_wgrad_workspace': (_ll, [_i, _i, _i, _i, _i, _i, _i]),
     'gt_conv2d_wgrad_f16': (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _ll, _vp, _ll, _vp]),
 }

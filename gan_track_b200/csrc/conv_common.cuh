@@ -32,6 +32,7 @@ struct ConvParams {
     // optional fused epilogue (fp16 output only): y = clamp(act(round_fp16(acc) + bias[co]) * gain), the bias_act that follows the
     // convolution in Conv2dLayer.forward (S3/training/networks_stylegan2.py:176-177); ep_act 0 = plain store
     const __half* ep_bias;
+    const __half* ep_add;            // optional residual with the layout of y: y = fp16(epilogue) + ep_add (DiscriminatorBlock's y.add_(x), :636)
     int ep_act;
     float ep_alpha, ep_gain, ep_clamp;
     int dbg_no_store;                // experiments only: run the whole pipeline but skip the global stores
@@ -74,6 +75,11 @@ __device__ __forceinline__ void conv_store32(const ConvParams& p, long long elem
                 if (p.ep_act == hot::LRELU) o = clamp_on ? hot::fwd<hot::LRELU, true>(u, hp) : hot::fwd<hot::LRELU, false>(u, hp);
                 else o = clamp_on ? hot::fwd<hot::LINEAR, true>(u, hp) : hot::fwd<hot::LINEAR, false>(u, hp);
                 h[k] = __float22half2_rn(o);
+            }
+            if (p.ep_add) {                                   // fp16 + fp16 -> fp16, round to nearest: what Tensor.add_ computes
+                const Vec16<__half> av = ld16(p.ep_add + elem_off + v * 8);
+#pragma unroll
+                for (int k = 0; k < 4; k++) h[k] = __hadd2(h[k], reinterpret_cast<const __half2*>(av.v)[k]);
             }
         }
         uint4 o;

@@ -253,7 +253,7 @@ extern "C" int gt_conv_pack_weight_f16(const void* w, long long s_co, long long 
 static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
                              long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
                              int pad, int transposed, int f32out, long long slab_stride, const void* ep_bias, int ep_act, float ep_alpha, float ep_gain,
-                             float ep_clamp, void* stream) {
+                             float ep_clamp, const void* ep_add, void* stream) {
     // f32out: fp16 operands, raw fp32 accumulators stored; with slab_stride > 0 the reduction is additionally split by kernel row
     // (one phase per row of taps, phase i writing its partial sum at y + i * slab_stride elements), which bounds the number of
     // accumulator updates per stored value (see csrc/conv_f16x3.cu)
@@ -261,6 +261,7 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     const int osz_al = f32out ? 4 : 8;
     GT_REQUIRE(ep_act == 0 || (!f32out && (ep_act == 1 || ep_act == 3)), "gt_conv2d_igemm: fused epilogue supports fp16 output with linear (1) or lrelu (3); got %d", ep_act);
     GT_REQUIRE(ep_bias == nullptr || (((uintptr_t)ep_bias) & 15) == 0, "gt_conv2d_igemm: epilogue bias must be 16-byte aligned");
+    GT_REQUIRE(ep_add == nullptr || (ep_act != 0 && (((uintptr_t)ep_add) & 15) == 0), "gt_conv2d_igemm: the residual needs the fused epilogue and 16-byte alignment");
     GT_REQUIRE(x && wpacked && y, "gt_conv2d_igemm_f16: null pointer");
     GT_REQUIRE(N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "gt_conv2d_igemm_f16: empty tensor");
     GT_REQUIRE(Cin % kel == 0 && Cout % 64 == 0, "gt_conv2d_igemm: Cin (%d) must be a multiple of %d and Cout (%d) of 64", Cin, kel, Cout);
@@ -279,6 +280,7 @@ static int conv2d_igemm_impl(const void* x, long long xs_n, long long xs_h, long
     p.y = y;
     p.f32out = f32out;
     p.ep_bias = (const __half*)ep_bias;
+    p.ep_add = (const __half*)ep_add;
     p.ep_act = ep_act;
     p.ep_alpha = ep_alpha;
     p.ep_gain = ep_gain;
@@ -410,7 +412,7 @@ extern "C" int gt_conv2d_igemm_f16(const void* x, long long xs_n, long long xs_h
                                    long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
                                    int pad, int transposed, void* stream) {
     return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, 0, nullptr, 0,
-                             0.f, 1.f, -1.f, stream);
+                             0.f, 1.f, -1.f, nullptr, stream);
 }
 
 // fp16 operands, fp32 output (raw accumulators): the tensor-core half of the fp16x3 route for the fp32 layers (csrc/conv_f16x3.cu).
@@ -419,7 +421,7 @@ extern "C" int gt_conv2d_igemm_f16_f32out(const void* x, long long xs_n, long lo
                                           long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
                                           int pad, int transposed, long long slab_stride, void* stream) {
     return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 1, slab_stride,
-                             nullptr, 0, 0.f, 1.f, -1.f, stream);
+                             nullptr, 0, 0.f, 1.f, -1.f, nullptr, stream);
 }
 
 // the same convolution with the layer's bias_act fused into the epilogue: y = clamp(act(conv + bias) * gain)
@@ -429,5 +431,17 @@ extern "C" int gt_conv2d_igemm_f16_bias_act(const void* x, long long xs_n, long 
                                             void* stream) {
     GT_REQUIRE(act == 1 || act == 3, "gt_conv2d_igemm_f16_bias_act: act must be linear (1) or lrelu (3); got %d", act);
     return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, 0, bias, act,
-                             alpha, gain, clamp, stream);
+                             alpha, gain, clamp, nullptr, stream);
+}
+
+// ... plus a residual: y = fp16(clamp(act(conv + bias) * gain)) + addend, addend fp16 with exactly the shape and strides of y
+// (DiscriminatorBlock.forward's `y.add_(x)`, S3/training/networks_stylegan2.py:636, folded into the skip convolution)
+extern "C" int gt_conv2d_igemm_f16_bias_act_add(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y, long long ys_n,
+                                                long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
+                                                int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain, float clamp,
+                                                const void* addend, void* stream) {
+    GT_REQUIRE(act == 1 || act == 3, "gt_conv2d_igemm_f16_bias_act_add: act must be linear (1) or lrelu (3); got %d", act);
+    GT_REQUIRE(addend != nullptr, "gt_conv2d_igemm_f16_bias_act_add: null addend");
+    return conv2d_igemm_impl(x, xs_n, xs_h, xs_w, wpacked, y, ys_n, ys_h, ys_w, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, transposed, 0, 0, bias, act,
+                             alpha, gain, clamp, addend, stream);
 }

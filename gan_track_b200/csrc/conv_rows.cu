@@ -315,6 +315,7 @@ bool gt_conv_rows_applicable(const ConvParams& p, int H, int W) {
     if (!g_conv_rows_enabled || p.Cin != 64 || p.Cout != 64 || p.nphases != 1 || p.in_stride != 1 || p.out_stride != 1) return false;
     const int mode = conv_mode(p);
     if (mode != CONV_F16 && mode != CONV_F16_EP) return false;
+    if (p.ep_add) return false;                  // the residual form of the epilogue lives in conv_store32 (halo / per-tap kernels)
     const ConvPhase& ph = p.ph[0];
     if (ph.ntaps != 9 || ph.OHp != H || ph.OWp != W || ph.y_off != 0) return false;
     bool seen[9] = {false, false, false, false, false, false, false, false, false};

@@ -152,11 +152,12 @@ def _fuse_profitable(input, weight, stride):
     return cin <= 64 or cin >= 512
 
 
-def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, clamp=None, stride=1, padding=0):
+def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, clamp=None, stride=1, padding=0, addend=None):
     """clamp(act(conv2d(input, weight) + bias) * gain), the tail of Conv2dLayer.forward (S3/training/networks_stylegan2.py:173-177).
     When the tcgen05 kernel takes the convolution (fp16 channels-last, channels multiples of 64) the bias / activation /
     gain / clamp run in its epilogue -- the activation tensor is written once instead of written, re-read and re-written --
-    otherwise this is exactly `bias_act(conv2d(...))`.  Gradients of any order: backward = bias_act's gradient Function
+    otherwise this is exactly `bias_act(conv2d(...))`.  `addend` (optional, the shape of the result): added to the result, in the
+    same epilogue when fused -- DiscriminatorBlock's `y.add_(x)` (:636) folded into the skip convolution.  Gradients of any order: backward = bias_act's gradient Function
     followed by the convolution's, both differentiable."""
     from . import bias_act as bias_act_mod
     from . import conv_igemm
@@ -164,14 +165,22 @@ def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, cl
     fusable = (fuse_bias_act is not False and conv_backend.allow_igemm and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
                and (fuse_bias_act is True or _fuse_profitable(input, weight, stride))
                and conv_igemm.covered(input, weight, False, (0, 0), stride, padding, 1) and (bias is None or bias.numel() % 8 == 0))
+    if addend is not None and fusable:
+        fusable = 'y' not in bias_act_mod.activation_funcs[act].ref
+    if addend is not None and fusable:
+        OH, OW = conv_igemm.out_size(input.shape[2], input.shape[3], weight.shape[2], weight.shape[3], stride[0], padding[0], False)
+        dense_cl = addend.dim() == 4 and addend.stride() == (OH * OW * weight.shape[0], 1, OW * weight.shape[0], weight.shape[0])
+        fusable = (addend.dtype == torch.float16 and tuple(addend.shape) == (input.shape[0], weight.shape[0], OH, OW) and dense_cl
+                   and addend.data_ptr() % 16 == 0)
     if not fusable:
         y = conv2d(input, weight, stride=stride, padding=padding)
-        return bias_act_mod.bias_act(y, bias, act=act, alpha=alpha, gain=gain, clamp=clamp)
+        y = bias_act_mod.bias_act(y, bias, act=act, alpha=alpha, gain=gain, clamp=clamp)
+        return y if addend is None else y.add_(addend)
     bias_act_mod._init()
     BA = bias_act_mod._bias_act_cuda(dim=1, act=act, alpha=alpha, gain=gain, clamp=clamp)
     spec, alpha_f, gain_f, clamp_f, trivial = BA.cfg
     Conv = _conv_fn(False, tuple(weight.shape), stride, padding, (0, 0), 1)
-    return _fused_fn(Conv, BA, stride, padding).apply(input, weight, bias)
+    return _fused_fn(Conv, BA, stride, padding).apply(input, weight, bias, addend)
 
 
 _fused_cache = dict()
@@ -187,14 +196,16 @@ def _fused_fn(Conv, BA, stride, padding):
 
     class ConvBiasAct(torch.autograd.Function):
         @staticmethod
-        def forward(ctx, x, w, b):
+        def forward(ctx, x, w, b, addend):
             bb = b.to(torch.float16).contiguous() if b is not None else None
             y = conv_igemm.igemm_forward(x, w, transpose=False, output_padding=(0, 0), stride=stride, padding=padding, groups=1,
-                                         epilogue=(bb, spec.cuda_idx, alpha, gain, clamp))
+                                         epilogue=(bb, spec.cuda_idx, alpha, gain, clamp, addend))
             assert y is not None
             conv_backend.stats['igemm'] += 1
             # like the reference's bias_act, `linear` saves no output (callers may then update it in place, e.g. y.add_(x) in
-            # DiscriminatorBlock.forward, S3/training/networks_stylegan2.py:636)
+            # DiscriminatorBlock.forward, S3/training/networks_stylegan2.py:636).  With a residual the stored tensor is act(...) + addend,
+            # which is not the activation's output: only `linear` (nothing saved) may carry one.
+            assert addend is None or 'y' not in spec.ref, 'a fused residual needs an activation whose gradient does not read its output'
             ctx.save_for_backward(x if w.requires_grad else _empty(x), w, y if 'y' in spec.ref else _empty(y))
             ctx.x_shape = x.shape
             ctx.has_bias = b is not None
@@ -221,7 +232,7 @@ def _fused_fn(Conv, BA, stride, padding):
                 dx = _conv_fn(True, tuple(w.shape), stride, padding, op, 1).apply(dpre, w)
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 dw = Conv.GradWeight.apply(dpre, x)
-            return dx, dw, db
+            return dx, dw, db, (dy if ctx.needs_input_grad[3] else None)      # the residual passes the gradient through
 
     _fused_cache[key] = ConvBiasAct
     return ConvBiasAct

@@ -29,14 +29,14 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
     if epilogue is not None:
         assert not transpose and groups == 1
         return conv2d_gradfix.conv2d_bias_act(x, w, epilogue['b'], act=epilogue['act'], gain=epilogue['gain'], clamp=epilogue['clamp'],
-                                              stride=stride, padding=padding)
+                                              stride=stride, padding=padding, addend=epilogue.get('addend'))
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
     return op(x, w, stride=stride, padding=padding, groups=groups)
 
 
 @misc.profiled_function
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, epilogue=None):
-    """`epilogue` (not in the reference): dict(b, act, gain, clamp) applied as bias_act to the result; only accepted when the
+    """`epilogue` (not in the reference): dict(b, act, gain, clamp[, addend]) applied as bias_act (+ residual) to the result; only accepted when the
     convolution is the LAST kernel of the case split (up == 1, groups == 1), where it is fused into the convolution."""
     assert isinstance(x, torch.Tensor) and x.ndim == 4
     assert isinstance(w, torch.Tensor) and w.ndim == 4 and w.dtype == x.dtype
@@ -102,4 +102,6 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     if epilogue is not None:
         from . import bias_act
         x = bias_act.bias_act(x, epilogue['b'], act=epilogue['act'], gain=epilogue['gain'], clamp=epilogue['clamp'])
+        if epilogue.get('addend') is not None:
+            x = x.add_(epilogue['addend'])
     return x

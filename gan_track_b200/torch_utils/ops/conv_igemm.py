@@ -189,8 +189,8 @@ def igemm_wgrad_f16x3(dy, x, weight_shape, *, transpose, output_padding, stride,
 
 
 def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, packed=None, epilogue=None):
-    """epilogue: None, or (bias fp16 [Cout] or None, act code 1 / 3, alpha, gain, clamp) -- the layer's bias_act fused into
-    the kernel's epilogue (fp16 only; the caller checks `covered` first)."""
+    """epilogue: None, or (bias fp16 [Cout] or None, act code 1 / 3, alpha, gain, clamp[, addend]) -- the layer's bias_act (and an optional
+    residual with the layout of the output, added after it) fused into the kernel's epilogue (fp16 only; the caller checks `covered` first)."""
     if epilogue is None and covered_fp32(x, w, transpose, output_padding, stride, padding, groups):
         return igemm_forward_f16x3(x, w, transpose=transpose, output_padding=output_padding, stride=stride, padding=padding, groups=groups)
     if not covered(x, w, transpose, output_padding, stride, padding, groups):
@@ -214,10 +214,18 @@ def igemm_forward(x, w, *, transpose, output_padding, stride, padding, groups, p
                                                N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0, _lib.stream_of(x)),
                        'gt_conv2d_igemm_f16')
         else:
-            b, act, alpha, gain, clamp = epilogue
-            _lib.check(lib.gt_conv2d_igemm_f16_bias_act(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,
-                                                        N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0,
-                                                        _lib.ptr(b), act, alpha, gain, clamp, _lib.stream_of(x)), 'gt_conv2d_igemm_f16_bias_act')
+            b, act, alpha, gain, clamp = epilogue[:5]
+            addend = epilogue[5] if len(epilogue) > 5 else None
+            if addend is None:
+                _lib.check(lib.gt_conv2d_igemm_f16_bias_act(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,
+                                                            N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0,
+                                                            _lib.ptr(b), act, alpha, gain, clamp, _lib.stream_of(x)), 'gt_conv2d_igemm_f16_bias_act')
+            else:
+                assert addend.shape == y.shape and addend.dtype == torch.float16 and addend.stride() == y.stride(), 'the residual must have the layout of the output'
+                _lib.check(lib.gt_conv2d_igemm_f16_bias_act_add(_lib.ptr(x), H * W * cin, W * cin, cin, _lib.ptr(packed), _lib.ptr(y), ys_n, ys_h, ys_w,
+                                                                N, H, W, cin, OH, OW, cout, kh, kw, stride[0], padding[0], 1 if transpose else 0,
+                                                                _lib.ptr(b), act, alpha, gain, clamp, _lib.ptr(addend), _lib.stream_of(x)),
+                           'gt_conv2d_igemm_f16_bias_act_add')
         _lib.count_launch()
     return y
 

@@ -215,7 +215,8 @@ class Conv2dLayer(torch.nn.Module):
             else:
                 self.register_buffer(name, value)
 
-    def forward(self, x, gain=1):
+    def forward(self, x, gain=1, addend=None):
+        # addend (not in the reference): a residual of the shape of the result, added to it (DiscriminatorBlock's shortcut.add_(x), :636)
         w = (self.weight * self.weight_gain).to(x.dtype)
         b = None if self.bias is None else self.bias.to(x.dtype)
         act = dict(act=self.activation, gain=self.act_gain * gain, clamp=_scaled(self.conv_clamp, gain))
@@ -223,13 +224,15 @@ class Conv2dLayer(torch.nn.Module):
         plain = self.up == 1 and self.down == 1
         if simple_act and plain and self.in_channels == 1 and self.weight.shape[2] == 1 and rgb.applicable(x, self.out_channels):
             # FromRGB on single-channel slices: outer product + bias_act in one pass, written channels-last (csrc/rgb.cu)
-            return rgb.fromrgb1(x, w.reshape(-1), b, **act)
+            y = rgb.fromrgb1(x, w.reshape(-1), b, **act)
+            return y if addend is None else y.add_(addend)
         resample = dict(f=self.resample_filter, up=self.up, down=self.down, padding=self.padding)
         if simple_act and self.up == 1 and x.is_cuda:
-            # the convolution is the last kernel of conv2d_resample: its bias_act rides in the convolution's epilogue
-            return conv2d_resample.conv2d_resample(x=x, w=w, flip_weight=True, epilogue=dict(b=b, **act), **resample)
+            # the convolution is the last kernel of conv2d_resample: its bias_act (and the residual) ride in the convolution's epilogue
+            return conv2d_resample.conv2d_resample(x=x, w=w, flip_weight=True, epilogue=dict(b=b, addend=addend, **act), **resample)
         y = conv2d_resample.conv2d_resample(x=x, w=w, flip_weight=(self.up == 1), **resample)
-        return bias_act.bias_act(y, b, **act)
+        y = bias_act.bias_act(y, b, **act)
+        return y if addend is None else y.add_(addend)
 
     def extra_repr(self):
         return _describe(self, 'in_channels', 'out_channels', 'activation', 'up', 'down')
@@ -492,9 +495,10 @@ class DiscriminatorBlock(torch.nn.Module):
             x = features if x is None else x + features
             img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
         if self.architecture == 'resnet':
-            shortcut = self.skip(x, gain=SQRT_HALF)
-            x = self.conv1(self.conv0(x), gain=SQRT_HALF)
-            x = shortcut.add_(x)
+            # shortcut.add_(main) of the reference (:636), with the residual handed to the skip layer: on fp16 CUDA tensors the addition
+            # runs in the epilogue of the skip convolution (the same fp16 sum of the two rounded branches, one pass over the result less)
+            main = self.conv1(self.conv0(x), gain=SQRT_HALF)
+            x = self.skip(x, gain=SQRT_HALF, addend=main)
         else:
             x = self.conv1(self.conv0(x))
         assert x.dtype == dtype

@@ -104,6 +104,12 @@ int gt_conv2d_igemm_f16_bias_act(const void* x, long long xs_n, long long xs_h, 
                                  long long ys_n, long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                                  int KH, int KW, int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain,
                                  float clamp, void* stream);
+/* ... plus a residual: y = round_fp16(clamp(act(round_fp16(conv) + bias) * gain)) + addend, addend fp16 with exactly the shape and strides of y
+ * (DiscriminatorBlock.forward's `y.add_(x)`, S3/training/networks_stylegan2.py:636, folded into the skip convolution). */
+int gt_conv2d_igemm_f16_bias_act_add(const void* x, long long xs_n, long long xs_h, long long xs_w, const void* wpacked, void* y,
+                                     long long ys_n, long long ys_h, long long ys_w, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                                     int KH, int KW, int stride, int pad, int transposed, const void* bias, int act, float alpha, float gain,
+                                     float clamp, const void* addend, void* stream);
 
 /* ---- fp32 convolutions on the tensor cores (fp16 x 3) -------------------------------------------------------------------
  * For the fp32 blocks of the networks (true-fp32 accuracy required; the reference runs them on the library with TF32 off,

@@ -220,3 +220,37 @@ def test_conv_bias_act_fused_epilogue_equals_unfused(shape, act, gain, clamp, bi
     for a, c in zip(outs[0][1:], outs[1][1:]):
         assert a.shape == c.shape
         assert _rel(a, c) <= 2e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 64, 16, 16, 1, 1, 0), (3, 64, 128, 33, 33, 1, 1, 0), (1, 64, 64, 40, 136, 3, 1, 1), (2, 128, 256, 32, 32, 3, 1, 1)])
+def test_conv_bias_act_fused_residual_equals_unfused(shape):
+    """conv -> bias_act(linear, gain, clamp) -> + residual (DiscriminatorBlock's shortcut.add_(x), S3/training/networks_stylegan2.py:636) with the
+    residual added in the convolution's epilogue: bit-identical to the three separate passes; gradients of x, w and the residual."""
+    from gan_track_b200.torch_utils.ops import conv2d_gradfix
+    N, ci, co, H, W, k, s, p = shape
+    g = torch.Generator(device='cuda').manual_seed(21)
+    x0 = torch.randn([N, ci, H, W], device='cuda', generator=g).to(torch.float16).contiguous(memory_format=torch.channels_last)
+    w0 = (torch.randn([co, ci, k, k], device='cuda', generator=g) / (ci * k * k) ** 0.5).to(torch.float16)
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    a0 = (torch.randn([N, co, OH, OW], device='cuda', generator=g) * 2).to(torch.float16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn([N, co, OH, OW], device='cuda', generator=g).to(torch.float16).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fused in (True, False):
+        old = conv2d_gradfix.fuse_bias_act
+        conv2d_gradfix.fuse_bias_act = fused
+        try:
+            x, w, a = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
+            before = dict(conv_backend_stats())
+            y = conv2d_gradfix.conv2d_bias_act(x, w, None, act='linear', gain=0.70710678, clamp=1.5, stride=s, padding=p, addend=a * 1.0)
+            outs.append([y.detach()] + [t.detach() for t in torch.autograd.grad(y, [x, w, a], dy)])
+        finally:
+            conv2d_gradfix.fuse_bias_act = old
+    assert torch.equal(outs[0][0], outs[1][0]), 'forward values must be bit-identical'
+    assert torch.equal(outs[0][3], outs[1][3]), 'the residual passes the gradient through'
+    for a, c in zip(outs[0][1:3], outs[1][1:3]):
+        assert _rel(a, c) <= TOL
+
+
+def conv_backend_stats():
+    from gan_track_b200.torch_utils.ops import conv_backend
+    return conv_backend.stats
