@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fuse-bias-act', action='store_true', help="A/B: the discriminator's bias_act runs in EVERY convolution epilogue (conv2d_gradfix.fuse_bias_act = True; default 'auto')")
+    ap.add_argument('--no-fuse-residual', action='store_true', help="A/B: the discriminator's residual add as its own pass (conv2d_gradfix.fuse_residual = False)")
     ap.add_argument('--no-fuse-bias-act', action='store_true', help="A/B: bias_act always as its own pass (conv2d_gradfix.fuse_bias_act = False)")
     ap.add_argument('--no-rooflines', action='store_true', help='skip the per-kernel roofline microbenchmarks (scaling runs)')
     ap.add_argument('--no-overlap', action='store_true')
@@ -376,6 +377,8 @@ def run_ours(args):
         _cg.fuse_bias_act = True
     if args.no_fuse_bias_act:
         _cg.fuse_bias_act = False
+    if args.no_fuse_residual:
+        _cg.fuse_residual = False
     conv_backend.allow_library = not args.no_library
     from gan_track_b200.torch_utils.ops import conv_igemm
     conv_igemm.call_log = {}
@@ -501,7 +504,7 @@ def run_ours(args):
                                    f'lazy R1 (every 16) + path-length (every 4), ADA={args.aug}', 'global_batch': global_batch, 'batch_gpu': batch_gpu,
                        'parallelism': f'dp{world}', 'phase_counts_in_timed_region': phase_counts,
                        'l2_policy': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush in the step loop',
-                       'conv_routes': conv_stats, 'allow_igemm': conv_backend.allow_igemm, 'allow_library': conv_backend.allow_library, 'fuse_bias_act': _cg.fuse_bias_act, 'cuda_graphs': not args.no_graphs, 'exchange': ('bucketed all-reduce on a side stream inside each phase graph, overlapped with backward' if trainer.graph_overlap
+                       'conv_routes': conv_stats, 'allow_igemm': conv_backend.allow_igemm, 'allow_library': conv_backend.allow_library, 'fuse_bias_act': _cg.fuse_bias_act, 'fuse_residual': _cg.fuse_residual, 'cuda_graphs': not args.no_graphs, 'exchange': ('bucketed all-reduce on a side stream inside each phase graph, overlapped with backward' if trainer.graph_overlap
                                                                        else 'one all-reduce of the flat gradient between two half-graphs') if world > 1 else 'none (1 GPU)',
                        'nccl_allreduce_alone': nccl_ms, 'dmain_one_pass': not args.two_pass_dmain, 'phase_ms': phase_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu_base, 'roofline_all': roof_all,

@@ -23,6 +23,7 @@ using namespace sm100;
 namespace {
 
 constexpr int NTHREADS = 192;
+constexpr int NTHREADS_EP = 320;     // fused bias_act (+ residual): eight epilogue warps, as in conv_igemm_halo2.cu / conv_rows.cu
 constexpr int SUB_W = 8, SUB_H = 16;   // one UMMA M=128 sub-tile: 16 rows of 8 pixels
 
 template <int BN, int MT, int SB, int NBUF>
@@ -57,7 +58,7 @@ __device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int t
 }
 
 template <int BN, int MT, int SB, int NBUF, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(MODE == CONV_F16_EP ? NTHREADS_EP : NTHREADS, 1) conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                        const ConvParams p, const int total_items) {
     typedef HaloSmem<BN, MT, SB, NBUF> L;
     extern __shared__ uint8_t smem_raw[];
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
         }
         for (int i = 0; i < NBUF; i++) {
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 4);   // one arrival per epilogue warp
+            mbar_init(&t_empty[i], MODE == CONV_F16_EP ? 8 : 4);   // one arrival per epilogue warp
         }
         for (int i = 0; i < SB; i++) {
             mbar_init(&b_full[i], 1);
@@ -177,6 +178,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
         __syncwarp();
     } else {
         const int q = warp & 3;
+        constexpr int CSETS = MODE == CONV_F16_EP ? 2 : 1;            // warp sets sharing a lane quarter take alternating column chunks
+        const int cset = MODE == CONV_F16_EP ? ((warp - 2) >> 2) : 0;
         const int m = q * 32 + lane;
         const int lw = m & (SUB_W - 1), lh = m >> 3;
         uint32_t t_it = 0;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_igemm_halo_kernel(const __gr
                 const long long yoff = (long long)it.n * p.ys_n + (long long)(a * p.out_stride + ph.off_y) * p.ys_h +
                                        (long long)(b * p.out_stride + ph.off_x) * p.ys_w + it.nt * BN + ph.y_off;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = cset; c < BN / 32; c += CSETS) {
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c * 32), r);
                     tmem_ld_wait();
@@ -230,7 +233,7 @@ int launch_halo_m(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvPara
     }
     int grid = gt_num_sms();
     if (grid > total_items) grid = total_items;
-    conv_igemm_halo_kernel<BN, MT, SB, NBUF, MODE><<<grid, NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
+    conv_igemm_halo_kernel<BN, MT, SB, NBUF, MODE><<<grid, MODE == CONV_F16_EP ? NTHREADS_EP : NTHREADS, L::TOTAL, stream>>>(tmA, tmB, p, total_items);
     GT_CUDA_LAUNCH_CHECK("gt_conv2d_igemm (halo)");
     return GT_OK;
 }

@@ -145,6 +145,9 @@ _env = _os.environ.get('GT_FUSE_BIAS_ACT', 'auto')
 fuse_bias_act = True if _env == '1' else (False if _env == '0' else 'auto')
 
 
+fuse_residual = True      # False: a residual (`addend`) is added by its own pass after the (possibly fused) bias_act -- A/B switch
+
+
 def _fuse_profitable(input, weight, stride):
     cout, cin, kh, kw = weight.shape
     if stride == (1, 1):
@@ -165,6 +168,8 @@ def conv2d_bias_act(input, weight, bias, act='linear', alpha=None, gain=None, cl
     fusable = (fuse_bias_act is not False and conv_backend.allow_igemm and act in _ACT_CODE and input.is_cuda and input.dtype == torch.float16
                and (fuse_bias_act is True or _fuse_profitable(input, weight, stride))
                and conv_igemm.covered(input, weight, False, (0, 0), stride, padding, 1) and (bias is None or bias.numel() % 8 == 0))
+    if addend is not None and not fuse_residual:
+        return conv2d_bias_act(input, weight, bias, act=act, alpha=alpha, gain=gain, clamp=clamp, stride=stride, padding=padding).add_(addend)
     if addend is not None and fusable:
         fusable = 'y' not in bias_act_mod.activation_funcs[act].ref
     if addend is not None and fusable:
