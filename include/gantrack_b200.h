@@ -149,8 +149,10 @@ int gt_f16x3_slab_reduce(const void* slabs, long long slab_stride, int nslabs, l
  * ds_r / ds_c.  Split-K partial sums go through `workspace` (fp32, at least gt_conv2d_wgrad_workspace(...) floats) and
  * are reduced in a fixed order, so the result is deterministic. */
 long long gt_conv2d_wgrad_workspace(int N, int UH, int UW, int UC, int SC, int KH, int KW);
-/* Kernel selection for gt_conv2d_wgrad_f16: 0 = automatic (halo-staged tap-paired kernel for stride-1 3x3, per-tap-row
- * kernel otherwise), 1 = per-tap-row kernel only.  Returns the previous value. */
+/* Kernel selection for gt_conv2d_wgrad_f16 (A/B switch of tools/test_igemm.py and the tests): 0 = automatic -- for 3x3 kernels the wide
+ * halo kernel (N = 128, two CTA types) with >= 128 U channels, else the halo-staged tap-paired kernel, both for stride 1 and for
+ * stride 2 / transposed stride 2 (parity planes); the per-tap-row kernel for 1x1 and small maps; 1 = per-tap-row kernel only; 2 = no
+ * stride-2 form of the tap-paired kernel; 3 = no wide kernel.  Returns the previous value. */
 int gt_conv_wgrad_config(int variant);
 int gt_conv2d_wgrad_f16(const void* u, long long us_n, long long us_h, long long us_w, int UH, int UW, int UC, const void* s,
                         long long ss_n, long long ss_h, long long ss_w, int SH, int SW, int SC, int N, int KH, int KW, int stride,
