@@ -177,6 +177,31 @@ def test_trainer_cuda_graph_mode_runs_and_captures():
         assert torch.isfinite(p).all()
 
 
+def test_full_width_training_step_needs_no_library_convolution():
+    """The 256x256 configuration of BASELINE config 2 (cbase 16384: 64 ... 512 channels, fp16 top-4 resolutions, ADA) with
+    `conv_backend.allow_library = False`: every convolution of all four phases -- fp16 blocks, the true-fp32 4^2 - 16^2 blocks (fp16 x 3),
+    forward, data and weight gradients, both double backwards -- must be taken by this package's tcgen05 kernels, else the step raises."""
+    from gan_track_b200.torch_utils.ops import conv_backend
+    from gan_track_b200.training import training_loop as tl
+    cfg = tl.claro_config(resolution=256, batch=4, num_gpus=1)
+    trainer = tl.Trainer(cfg, rank=0, device='cuda', use_graphs=False)
+    real = torch.rand(4, 1, 256, 256) * 255
+    c = torch.nn.functional.one_hot(torch.tensor([0, 1, 1, 0]), 2).float()
+    before = dict(conv_backend.stats)
+    old = conv_backend.allow_library
+    conv_backend.allow_library = False
+    try:
+        trainer.train_step(real, c)              # iteration 0 runs Gmain, Greg, Dmain and Dreg
+        torch.cuda.synchronize()
+    finally:
+        conv_backend.allow_library = old
+    assert trainer.phase_counts == {'Gmain': 1, 'Greg': 1, 'Dmain': 1, 'Dreg': 1}
+    assert conv_backend.stats['library'] == before['library'] and conv_backend.stats['library_wgrad'] == before['library_wgrad']
+    assert conv_backend.stats['igemm'] > before['igemm'] + 100 and conv_backend.stats['igemm_wgrad'] > before['igemm_wgrad'] + 30
+    for p in list(trainer.G.parameters()) + list(trainer.D.parameters()):
+        assert torch.isfinite(p).all()
+
+
 @pytest.mark.parametrize('fp32,tol', [(True, 2e-4), (False, 2e-2)])
 def test_dmain_merged_pass_equals_two_passes_cuda(fp32, tol):
     """Dmain as one discriminator pass over the interleaved [generated, real] batch vs the reference's two passes, on the
